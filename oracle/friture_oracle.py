@@ -1,0 +1,313 @@
+"""NumPy/SciPy restatement of the reference's per-chunk spectral hot path.
+
+TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  Every function cites the
+reference file:line it restates (paths relative to the reference root).  All arithmetic
+is float64, like the reference (friture/audiobackend.py:466-468 widens the device's
+float32 to float64 before anything else touches it).
+
+The FFTs are ``numpy.fft`` (pocketfft), i.e. the very third-party routine the reference
+calls (friture/audioproc.py:23,44; friture/signal/correlation.py:21,34-41); the IIR
+recursions are restated as a direct-form-II-transposed loop, run either through
+``scipy.signal.lfilter`` (same recursion, verified bit-identical to the reference's
+pure-Python loop in tests/test_oracle_vs_reference.py) or through the plain-C loop in
+``oracle/iir_df2t.c``.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+SAMPLING_RATE = 48000      # friture/audiobackend.py:31
+FRAMES_PER_BUFFER = 512    # friture/audiobackend.py:32
+NOCTAVE = 9                # friture/filter.py:7
+
+
+# --------------------------------------------------------------------------- STFT
+def hann_window(n_fft: int) -> np.ndarray:
+    """Symmetric Hann, 0.5*(1-cos(2*pi*n/(N-1))): friture/audioproc.py:76-81."""
+    n = np.arange(0, n_fft)
+    return 0.5 * (1.0 - np.cos(2 * np.pi * n / (n_fft - 1)))
+
+
+def analyzelive(samples: np.ndarray, window: np.ndarray | None = None) -> np.ndarray:
+    """|rfft(x*w)|^2 / N^2: friture/audioproc.py:42-50,73-74."""
+    samples = np.asarray(samples, dtype=np.float64)
+    n_fft = samples.shape[-1]
+    if window is None:
+        window = hann_window(n_fft)
+    fft = np.fft.rfft(samples * window)
+    return (fft * fft.conjugate()).real / float(n_fft) ** 2
+
+
+def log_spectrogram(sp: np.ndarray) -> np.ndarray:
+    """10*log10(sp + 1e-30): friture/spectrogram.py:119-125, friture/spectrum.py:95-101."""
+    return 10.0 * np.log10(sp + 1e-30)
+
+
+def frame_count(n_samples: int, n_fft: int, hop: int) -> int:
+    """Number of whole frames in a stream of n_samples (first frame = samples [0, n_fft))."""
+    if n_samples < n_fft:
+        return 0
+    return (n_samples - n_fft) // hop + 1
+
+
+def stft_power(x: np.ndarray, n_fft: int, hop: int) -> np.ndarray:
+    """Framing loop of friture/spectrogram.py:131-159 (spectrum.py:125-155) for one stream.
+
+    Frame i is the n_fft samples ending at ``n_fft + i*hop`` (the reference's
+    ``data_indexed(old_index, fft_size)`` returns the samples *ending* at old_index,
+    friture/ringbuffer.py:87-99, and ``old_index += int(needed)`` per column).  Returns
+    power[frames, n_fft//2+1] (time-major; the reference stores the transpose,
+    spectrogram.py:147,157)."""
+    x = np.asarray(x, dtype=np.float64)
+    w = hann_window(n_fft)
+    nf = frame_count(x.shape[-1], n_fft, hop)
+    out = np.empty((nf, n_fft // 2 + 1), dtype=np.float64)
+    for i in range(nf):
+        out[i] = analyzelive(x[i * hop: i * hop + n_fft], w)
+    return out
+
+
+def stft_power_batch(x: np.ndarray, n_fft: int, hop: int) -> np.ndarray:
+    """Vectorised form of :func:`stft_power` for x[C, T] (same arithmetic, one rfft call)."""
+    x = np.asarray(x, dtype=np.float64)
+    if x.ndim == 1:
+        x = x[None, :]
+    nf = frame_count(x.shape[-1], n_fft, hop)
+    w = hann_window(n_fft)
+    idx = np.arange(nf)[:, None] * hop + np.arange(n_fft)[None, :]
+    fft = np.fft.rfft(x[:, idx] * w, axis=-1)
+    return (fft * fft.conjugate()).real / float(n_fft) ** 2
+
+
+def weighting_tables(f: np.ndarray, eps: float = 1e-50):
+    """A/B/C psychoacoustic weighting in dB: friture/audioproc.py:83-96 (eps=1e-50);
+    friture/octavefilters.py:76-82 uses the same formulas with no eps (pass eps=0)."""
+    f = np.asarray(f, dtype=np.float64)
+    Rc = 12200. ** 2 * f ** 2 / ((f ** 2 + 20.6 ** 2) * (f ** 2 + 12200. ** 2))
+    Rb = 12200. ** 2 * f ** 3 / ((f ** 2 + 20.6 ** 2) * (f ** 2 + 12200. ** 2) * ((f ** 2 + 158.5 ** 2) ** 0.5))
+    Ra = 12200. ** 2 * f ** 4 / ((f ** 2 + 20.6 ** 2) * (f ** 2 + 12200. ** 2) * ((f ** 2 + 107.7 ** 2) ** 0.5) * ((f ** 2 + 737.9 ** 2) ** 0.5))
+    C = 0.06 + 20. * np.log10(Rc + eps)
+    B = 0.17 + 20. * np.log10(Rb + eps)
+    A = 2.0 + 20. * np.log10(Ra + eps)
+    return A, B, C
+
+
+# --------------------------------------------------------------------------- IIR
+def lfilter_df2t(b, a, x, zi):
+    """Direct-form-II-transposed IIR with carried state: friture/signal/lfilter.py:85-147.
+
+    ``scipy.signal.lfilter`` runs the identical recursion (a[0]==1 in every reference
+    coefficient set, friture/generated_filters.py), bit-for-bit equal to the reference's
+    Python loop (checked in tests/test_oracle_vs_reference.py)."""
+    from scipy.signal import lfilter
+    y, zf = lfilter(np.asarray(b, dtype=np.float64), np.asarray(a, dtype=np.float64),
+                    np.asarray(x, dtype=np.float64), zi=np.asarray(zi, dtype=np.float64))
+    return y, zf
+
+
+def lfilter_df2t_loop(b, a, x, zi):
+    """Literal scalar loop of friture/signal/lfilter.py:131-139 (slow; small cases only)."""
+    b = [float(v) for v in b]
+    a = [float(v) for v in a]
+    z = [float(v) for v in zi]
+    nb = len(b)
+    y = np.empty(len(x), dtype=np.float64)
+    for k, xk in enumerate(np.asarray(x, dtype=np.float64).tolist()):
+        yk = z[0] + b[0] * xk
+        y[k] = yk
+        for n in range(nb - 2):
+            z[n] = z[n + 1] + xk * b[n + 1] - yk * a[n + 1]
+        z[nb - 2] = xk * b[nb - 1] - yk * a[nb - 1]
+    return y, np.array(z)
+
+
+def decimate(bdec, adec, x, zi=None):
+    """Low-pass then keep even indices: friture/signal/decimate.py:27-42."""
+    if len(x) == 0:
+        raise Exception("Filter input is too small")
+    if zi is None:
+        zi = np.zeros(max(len(bdec), len(adec)) - 1)
+    y, zf = lfilter_df2t(bdec, adec, x, zi)
+    return y[::2], zf
+
+
+def decimate_multiple(ndec, bdec, adec, x, zis):
+    """N-fold decimation with carried states: friture/signal/decimate.py:45-71."""
+    x = np.asarray(x, dtype=np.float64)
+    if x.size == 0:
+        return x, zis
+    zfs = []
+    for i in range(ndec):
+        x, zf = decimate(bdec, adec, x, None if zis is None else zis[i])
+        zfs.append(zf)
+    return x, (None if zis is None else zfs)
+
+
+def bank_filtic(bdec, adec, boct, aoct, noctave=NOCTAVE):
+    """Zero initial states, ordered band(bpo-1..0) then decimator per stage:
+    friture/filter.py:121-133."""
+    zis = []
+    for _ in range(noctave):
+        for i in range(len(boct))[::-1]:
+            zis.append(np.zeros(max(len(boct[i]), len(aoct[i])) - 1))
+        zis.append(np.zeros(max(len(bdec), len(adec)) - 1))
+    return zis
+
+
+def octave_filter_bank_decimation(bdec, adec, boct, aoct, x, zis, noctave=NOCTAVE):
+    """Multi-rate IIR bank, the numerical oracle of the filterbank row:
+    friture/filter.py:86-118.  Returns (y[nbands] ragged, dec[nbands], zfs)."""
+    bpo = len(boct)
+    nb = noctave * bpo
+    y = [None] * nb
+    dec = [0] * nb
+    zfs = []
+    x_dec = np.asarray(x, dtype=np.float64)
+    m = 0
+    k = nb - 1
+    for j in range(noctave):
+        for i in range(bpo)[::-1]:
+            filt, zf = lfilter_df2t(boct[i], aoct[i], x_dec, zis[m])
+            m += 1
+            zfs.append(zf)
+            y[k] = filt
+            dec[k] = 2 ** j
+            k -= 1
+        x_dec, zf = decimate(bdec, adec, x_dec, zis[m])
+        m += 1
+        zfs.append(zf)
+    return y, dec, zfs
+
+
+def get_decs(bpo, noctave=NOCTAVE):
+    """friture/octavefilters.py:60-63."""
+    return [2 ** j for j in range(noctave)[::-1] for _ in range(bpo)]
+
+
+def octave_frequencies(total_bands_count, bands_per_octave):
+    """Band centre / edge frequencies: friture/filter.py:39-54."""
+    f0 = 1000.
+    b = 1. / bands_per_octave
+    imax = total_bands_count // 2
+    if total_bands_count % 2 == 0:
+        i = np.arange(-imax, imax)
+    else:
+        i = np.arange(-imax, imax + 1)
+    fi = f0 * 2 ** (i * b)
+    return fi, fi * np.sqrt(2 ** (-b)), fi * np.sqrt(2 ** b)
+
+
+# --------------------------------------------------------------------------- smoothing
+def smoothing_alpha(response_time, rate):
+    """alpha so that the newest n = T*rate samples carry 65 % of the weight:
+    friture/octavespectrum.py:140-156 (rate = fs/dec), friture/spectrum.py:196-218
+    (rate = fs/hop)."""
+    w = 0.65
+    n = response_time * rate
+    return 1. - (1. - w) ** (1. / (n + 1))
+
+
+def smoothing_kernel(alpha, n):
+    """(1-alpha)^(n-1 .. 0): friture/octavespectrum.py:75-79, friture/spectrum.py:220-222."""
+    return (1. - alpha) ** np.arange(int(n) - 1, -1, -1)
+
+
+def exp_smoothed_value(kernel, alpha, data, previous):
+    """Block form of s <- alpha*x + (1-alpha)*s: friture/signal/exp_smoothing.py:11-56."""
+    N = data.shape[0]
+    Nk = kernel.shape[0]
+    if N > Nk:
+        N = Nk
+        a = 0.0
+    else:
+        a = (1.0 - alpha) ** N
+    if N == 0:
+        return previous
+    conv = np.dot(kernel[Nk - N:Nk], data[:N])
+    return float(alpha * conv + previous * a)
+
+
+def exp_smoothed_value_2d(kernel, alpha, data, previous):
+    """Row-wise block smoothing: friture/signal/exp_smoothing.py:59-107."""
+    Nf, Nt = data.shape
+    Nk = kernel.shape[0]
+    if Nt > Nk:
+        Nt = Nk
+        a = 0.0
+    else:
+        a = (1.0 - alpha) ** Nt
+    if Nt == 0:
+        return np.array(previous, copy=True)
+    conv = data[:, :Nt] @ kernel[Nk - Nt:Nk]
+    return alpha * conv + previous * a
+
+
+class OctaveSpectrumOracle:
+    """What OctaveSpectrum_Widget.handle_new_data does per chunk, with the IIR bank
+    (friture/octavespectrum.py:91-121,140-156 around friture/filter.py:86-118):
+    filter -> y**2 -> exp_smoothed_value per band -> 10*log10(sp+1e-30) (+ weighting)."""
+
+    def __init__(self, bdec, adec, boct, aoct, response_time=1.0, noctave=NOCTAVE):
+        self.bdec = np.asarray(bdec, dtype=np.float64)
+        self.adec = np.asarray(adec, dtype=np.float64)
+        self.boct = [np.asarray(v, dtype=np.float64) for v in boct]
+        self.aoct = [np.asarray(v, dtype=np.float64) for v in aoct]
+        self.noctave = noctave
+        self.bpo = len(boct)
+        self.nbands = noctave * self.bpo
+        self.zis = bank_filtic(self.bdec, self.adec, self.boct, self.aoct, noctave)
+        decs = get_decs(self.bpo, noctave)
+        self.decs = decs
+        self.alphas = [smoothing_alpha(response_time, SAMPLING_RATE / d) for d in decs]
+        self.kernels = [smoothing_kernel(a, 2 * 4096 / d) for a, d in zip(self.alphas, decs)]
+        self.dispbuffers = [0.0] * self.nbands
+
+    def filter(self, x):
+        y, dec, self.zis = octave_filter_bank_decimation(
+            self.bdec, self.adec, self.boct, self.aoct, x, self.zis, self.noctave)
+        return y, dec
+
+    def push(self, x):
+        """One chunk -> (smoothed band energies[nbands], dB[nbands], y)."""
+        y, _ = self.filter(x)
+        sp = [exp_smoothed_value(k, a, yy ** 2, old)
+              for yy, k, a, old in zip(y, self.kernels, self.alphas, self.dispbuffers)]
+        self.dispbuffers = sp
+        sp = np.array(sp)
+        return sp, 10 * np.log10(sp + 1e-30), y
+
+
+# --------------------------------------------------------------------------- GCC-PHAT
+def generalized_cross_correlation(d0, d1):
+    """GCC-PHAT: friture/signal/correlation.py:24-43 (works on copies: the reference
+    subtracts the means in place, a side effect that is not part of the result)."""
+    d0 = np.array(d0, dtype=np.float64)
+    d1 = np.array(d1, dtype=np.float64)
+    d0 -= d0.mean()
+    d1 -= d1.mean()
+    window = np.hanning(len(d0))
+    D0 = np.fft.rfft(d0 * window)
+    D1 = np.fft.rfft(d1 * window)
+    G = D0.conjugate() * D1
+    absG = np.abs(G)
+    m = max(absG)
+    W = 1. / (1e-10 * m + absG)
+    return np.fft.irfft(W * G)
+
+
+def delay_peak(xcorr, old_xcorr=None, alpha=0.3):
+    """Smoothing + peak pick of friture/delay_estimator.py:134-142.
+    Returns (index, extremum value, smoothed xcorr)."""
+    if old_xcorr is not None and old_xcorr.shape == xcorr.shape:
+        sm = alpha * xcorr + (1. - alpha) * old_xcorr
+    else:
+        sm = xcorr
+    i = int(np.argmax(np.abs(sm)))
+    return i, float(sm[i]), sm
+
+
+# --------------------------------------------------------------------------- spectrum widget reductions
+def harmonic_product_spectrum(sp):
+    """sp[:h]*sp[::2][:h]*sp[::3][:h], h=len//3: friture/spectrum.py:103-123."""
+    h = sp.shape[0] // 3
+    return sp[:h] * sp[::2][:h] * sp[::3][:h]
