@@ -1,0 +1,141 @@
+// Handle lifecycle, error reporting and the host-staging pipeline of libfrt_b200.so.
+#include <cstdarg>
+#include <mutex>
+
+#include "frt_internal.cuh"
+
+static std::string g_create_error;
+static std::mutex g_create_mutex;
+
+int frt_fail(frt_ctx *h, int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (h) {
+        h->err = buf;
+    } else {
+        std::lock_guard<std::mutex> lock(g_create_mutex);
+        g_create_error = buf;
+    }
+    return code;
+}
+
+extern "C" int frt_version(void) { return 100; }
+
+extern "C" int frt_create(int device, frt_handle *out) {
+    if (!out) return frt_fail(nullptr, FRT_EINVAL, "frt_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0)
+        return frt_fail(nullptr, FRT_ECUDA,
+                        "frt_create: no usable CUDA device (%s); friture_b200 has no CPU fallback",
+                        e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= count)
+        return frt_fail(nullptr, FRT_EINVAL, "frt_create: device %d out of range [0,%d)", device,
+                        count);
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess)
+        return frt_fail(nullptr, FRT_ECUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major < 10)
+        return frt_fail(nullptr, FRT_ECUDA,
+                        "frt_create: device %d is sm_%d%d; this library is built for sm_100a only",
+                        device, prop.major, prop.minor);
+    frt_ctx *h = new (std::nothrow) frt_ctx();
+    if (!h) return frt_fail(nullptr, FRT_ENOMEM, "frt_create: out of host memory");
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    *out = h;
+    return FRT_OK;
+}
+
+static void pipe_release(frt_ctx *h) {
+    HostPipe &p = h->pipe;
+    for (int i = 0; i < 2; i++) {
+        if (p.d_in[i]) cudaFree(p.d_in[i]);
+        if (p.d_out[i]) cudaFree(p.d_out[i]);
+        if (p.ev_in[i]) cudaEventDestroy(p.ev_in[i]);
+        if (p.ev_cmp[i]) cudaEventDestroy(p.ev_cmp[i]);
+        if (p.ev_out[i]) cudaEventDestroy(p.ev_out[i]);
+    }
+    if (p.s_in) cudaStreamDestroy(p.s_in);
+    if (p.s_cmp) cudaStreamDestroy(p.s_cmp);
+    if (p.s_out) cudaStreamDestroy(p.s_out);
+    p = HostPipe();
+}
+
+int frt_pipe_ensure(frt_ctx *h, size_t in_bytes, size_t out_bytes) {
+    HostPipe &p = h->pipe;
+    if (!p.s_in) {
+        FRT_CUDA(h, cudaStreamCreateWithFlags(&p.s_in, cudaStreamNonBlocking));
+        FRT_CUDA(h, cudaStreamCreateWithFlags(&p.s_cmp, cudaStreamNonBlocking));
+        FRT_CUDA(h, cudaStreamCreateWithFlags(&p.s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            FRT_CUDA(h, cudaEventCreateWithFlags(&p.ev_in[i], cudaEventDisableTiming));
+            FRT_CUDA(h, cudaEventCreateWithFlags(&p.ev_cmp[i], cudaEventDisableTiming));
+            FRT_CUDA(h, cudaEventCreateWithFlags(&p.ev_out[i], cudaEventDisableTiming));
+        }
+    }
+    if (in_bytes > p.in_bytes) {
+        for (int i = 0; i < 2; i++) {
+            if (p.d_in[i]) cudaFree(p.d_in[i]);
+            p.d_in[i] = nullptr;
+            FRT_CUDA(h, cudaMalloc(&p.d_in[i], in_bytes));
+        }
+        p.in_bytes = in_bytes;
+    }
+    if (out_bytes > p.out_bytes) {
+        for (int i = 0; i < 2; i++) {
+            if (p.d_out[i]) cudaFree(p.d_out[i]);
+            p.d_out[i] = nullptr;
+            FRT_CUDA(h, cudaMalloc(&p.d_out[i], out_bytes));
+        }
+        p.out_bytes = out_bytes;
+    }
+    return FRT_OK;
+}
+
+extern "C" int frt_destroy(frt_handle h) {
+    if (!h) return FRT_OK;
+    DeviceGuard g(h->device);
+    cudaDeviceSynchronize();
+    if (h->stft.win_dev) cudaFree(h->stft.win_dev);
+    if (h->stft.tw_dev) cudaFree(h->stft.tw_dev);
+    if (h->stft.post_dev) cudaFree(h->stft.post_dev);
+    frt_bank_release(h);
+    frt_gcc_release(h);
+    pipe_release(h);
+    delete h;
+    return FRT_OK;
+}
+
+extern "C" const char *frt_last_error(frt_handle h) {
+    if (h) return h->err.c_str();
+    std::lock_guard<std::mutex> lock(g_create_mutex);
+    return g_create_error.c_str();
+}
+
+extern "C" int frt_device_sm_count(frt_handle h) { return h ? h->sm_count : 0; }
+
+extern "C" int64_t frt_launch_count(frt_handle h) { return h ? h->launches : 0; }
+
+extern "C" int frt_host_alloc(frt_handle h, size_t bytes, void **out) {
+    if (!h || !out) return frt_fail(h, FRT_EINVAL, "frt_host_alloc: NULL argument");
+    DeviceGuard g(h->device);
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable);
+    if (e != cudaSuccess)
+        return frt_fail(h, FRT_ENOMEM, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e));
+    return FRT_OK;
+}
+
+extern "C" int frt_host_free(frt_handle h, void *p) {
+    if (!p) return FRT_OK;
+    if (!h) return FRT_EINVAL;
+    DeviceGuard g(h->device);
+    FRT_CUDA(h, cudaFreeHost(p));
+    return FRT_OK;
+}

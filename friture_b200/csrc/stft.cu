@@ -1,0 +1,523 @@
+// Fused STFT for sm_100a: Hann window -> real FFT -> |X|^2/N^2 -> (10*log10(.+1e-30)), one pass
+// HBM -> HBM, no cuFFT.  Stands behind audioproc.analyzelive (friture/audioproc.py:42-50), the
+// framing loops of friture/spectrogram.py:131-159 / friture/spectrum.py:125-155 and
+// log_spectrogram (friture/spectrogram.py:119-125).
+//
+// A real FFT of N points is computed as a complex FFT of M = N/2 points on
+// z[n] = x[2n] + j*x[2n+1], followed by the split step
+//     X[k]   = (E + T)/2,  X[M-k] = conj(E - T)/2,
+//     E = Z[k] + conj(Z[M-k]),  O = Z[k] - conj(Z[M-k]),  T = (-j*W_N^k) * O.
+//
+// Fast path (N = 2048, the benchmark's size): ONE WARP PER FRAME, M = 1024 = 32 x 32.
+//   lane t holds z[32*n1 + t] (n1 = 0..31) in registers -> radix-32 DFT over n1 in registers
+//   -> twiddle W_M^(k1*t) -> 32x32 transpose through a warp-private padded smem tile
+//   -> radix-32 DFT over n2 -> lane t holds X[t + 32*k2]; the split partner X[M-k] lives in
+//   lane (32-t)%32 and is fetched with warp shuffles.  Only __syncwarp(), no block barrier.
+//   Complex arithmetic is written on float2 so ptxas emits packed FADD2/FMUL2/FFMA2 (one issue
+//   slot per complex add, two per complex multiply).
+// Generic path (every other size 32..16384): one CTA per frame, Stockham radix-4 (+ one radix-2
+//   pass when log2(M) is odd) ping-ponging between two shared-memory buffers.
+#include <cmath>
+
+#include "frt_internal.cuh"
+
+namespace {
+
+constexpr float kLog10Scale = 3.01029995663981195f;   // 10 / log2(10)
+constexpr float kEps = 1e-30f;                        // friture/spectrogram.py:124
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) {
+    return __fadd2_rn(a, make_float2(-b.x, -b.y));
+}
+// a * w
+__device__ __forceinline__ float2 cmul(float2 a, float2 w) {
+    float2 t = __fmul2_rn(a, make_float2(w.x, w.x));
+    return __ffma2_rn(make_float2(-a.y, a.x), make_float2(w.y, w.y), t);
+}
+// a * (-j)
+__device__ __forceinline__ float2 mul_mj(float2 a) { return make_float2(a.y, -a.x); }
+
+// cos/sin(2*pi*i/32), i = 0..15
+__device__ __forceinline__ constexpr float cos32(int i) {
+    constexpr float t[16] = {1.0f,
+                             0.98078528040323044913f,
+                             0.92387953251128675613f,
+                             0.83146961230254523708f,
+                             0.70710678118654752440f,
+                             0.55557023301960222474f,
+                             0.38268343236508977173f,
+                             0.19509032201612826785f,
+                             0.0f,
+                             -0.19509032201612826785f,
+                             -0.38268343236508977173f,
+                             -0.55557023301960222474f,
+                             -0.70710678118654752440f,
+                             -0.83146961230254523708f,
+                             -0.92387953251128675613f,
+                             -0.98078528040323044913f};
+    return t[i];
+}
+__device__ __forceinline__ constexpr float sin32(int i) {
+    constexpr float t[16] = {0.0f,
+                             0.19509032201612826785f,
+                             0.38268343236508977173f,
+                             0.55557023301960222474f,
+                             0.70710678118654752440f,
+                             0.83146961230254523708f,
+                             0.92387953251128675613f,
+                             0.98078528040323044913f,
+                             1.0f,
+                             0.98078528040323044913f,
+                             0.92387953251128675613f,
+                             0.83146961230254523708f,
+                             0.70710678118654752440f,
+                             0.55557023301960222474f,
+                             0.38268343236508977173f,
+                             0.19509032201612826785f};
+    return t[i];
+}
+
+__host__ __device__ constexpr int brev5(int r) {
+    return ((r & 1) << 4) | ((r & 2) << 2) | (r & 4) | ((r & 8) >> 2) | ((r & 16) >> 4);
+}
+
+// In-register radix-32 DFT (decimation in frequency, fully unrolled): v[r] <- bin brev5(r).
+__device__ __forceinline__ void dft32(float2 (&v)[32]) {
+#pragma unroll
+    for (int len = 32; len >= 2; len >>= 1) {
+        const int half = len >> 1;
+        const int tstep = 32 / len;
+#pragma unroll
+        for (int base = 0; base < 32; base += len) {
+#pragma unroll
+            for (int i = 0; i < half; i++) {
+                const float2 a = v[base + i], b = v[base + i + half];
+                v[base + i] = cadd(a, b);
+                const float2 d = csub(a, b);
+                const int ti = i * tstep;
+                if (ti == 0)
+                    v[base + i + half] = d;
+                else if (ti == 8)
+                    v[base + i + half] = mul_mj(d);
+                else
+                    v[base + i + half] = cmul(d, make_float2(cos32(ti), -sin32(ti)));
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ float lg2_fast(float v) {
+    // MUFU.LG2; the argument is always >= 1e-30 (normal), so the denormal fix-up of
+    // __log2f is not needed
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+
+template <int MODE>
+__device__ __forceinline__ float finish(float mag2, float scale) {
+    // mag2*scale = |X|^2/N^2 (audioproc.py:49-50); log mode: spectrogram.py:119-125
+    if (MODE == FRT_STFT_POWER) return mag2 * scale;
+    return kLog10Scale * lg2_fast(fmaf(mag2, scale, kEps));
+}
+
+// ------------------------------------------------------------------------------------------
+// Fast path, N = 2048.
+constexpr int FAST_N = 2048;
+constexpr int FAST_M = 1024;
+constexpr int FAST_WARPS = 16;
+constexpr int FAST_TILE = 32 * 33;   // padded 32x32 complex tile per warp
+constexpr int FAST_POST = 17 * 32;
+constexpr size_t FAST_SMEM =
+    sizeof(float2) * (FAST_M + FAST_M + FAST_POST + (size_t)FAST_WARPS * FAST_TILE);
+
+template <int MODE, int VEC>
+__global__ void __launch_bounds__(FAST_WARPS * 32, 1)
+stft2048_kernel(const float *__restrict__ x, long long x_stride, long long n_frames, int hop,
+                float *__restrict__ out, long long out_stride_c, long long out_stride_f,
+                const float2 *__restrict__ win2, const float2 *__restrict__ tw,
+                const float2 *__restrict__ post, long long total_items) {
+    extern __shared__ float2 smem[];
+    float2 *s_win = smem;                 // [1024]  (w[2n], w[2n+1])
+    float2 *s_tw = s_win + FAST_M;        // [32][32] W_1024^(k1*t)
+    float2 *s_post = s_tw + FAST_M;       // [17][32] U[t + 32 m] = -j W_2048^(t+32m)
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    float2 *s_x = s_post + FAST_POST + warp * FAST_TILE;
+
+    for (int i = threadIdx.x; i < FAST_M; i += blockDim.x) {
+        s_win[i] = win2[i];
+        s_tw[i] = tw[i];
+    }
+    for (int i = threadIdx.x; i < FAST_POST; i += blockDim.x) s_post[i] = post[i];
+    __syncthreads();
+
+    // contiguous range of (channel, frame) items per warp: consecutive frames of a channel
+    // stay on one SM so the overlapping half of each frame is re-read from L1/L2, not HBM
+    const long long warps_total = (long long)gridDim.x * FAST_WARPS;
+    const long long gw = (long long)blockIdx.x * FAST_WARPS + warp;
+    const long long per = (total_items + warps_total - 1) / warps_total;
+    long long item = gw * per;
+    long long item_end = item + per;
+    if (item_end > total_items) item_end = total_items;
+    const float scale = 1.0f / (4.0f * (float)FAST_N * (float)FAST_N);
+    const int src_lane = (32 - lane) & 31;
+
+    long long c = (item < item_end) ? item / n_frames : 0;
+    long long f = item - c * n_frames;
+    for (; item < item_end; item++) {
+        const float *p = x + c * x_stride + f * hop;
+        float2 v[32];
+        if (VEC) {
+            const float2 *p2 = reinterpret_cast<const float2 *>(p);
+#pragma unroll
+            for (int n1 = 0; n1 < 32; n1++) v[n1] = __ldg(p2 + 32 * n1 + lane);
+        } else {
+#pragma unroll
+            for (int n1 = 0; n1 < 32; n1++) {
+                v[n1].x = __ldg(p + 64 * n1 + 2 * lane);
+                v[n1].y = __ldg(p + 64 * n1 + 2 * lane + 1);
+            }
+        }
+#pragma unroll
+        for (int n1 = 0; n1 < 32; n1++) v[n1] = __fmul2_rn(v[n1], s_win[32 * n1 + lane]);
+
+        dft32(v);   // v[r] = sum_n1 z[32 n1 + t] W_32^(n1 k1), k1 = brev5(r)
+#pragma unroll
+        for (int r = 0; r < 32; r++) {
+            const int k1 = brev5(r);
+            const float2 val = (k1 == 0) ? v[r] : cmul(v[r], s_tw[k1 * 32 + lane]);
+            s_x[k1 * 33 + lane] = val;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int n2 = 0; n2 < 32; n2++) v[n2] = s_x[lane * 33 + n2];
+        __syncwarp();
+        dft32(v);   // v[r] = Z[lane + 32*brev5(r)]
+
+        float *o = out + c * out_stride_c + f * out_stride_f;
+#pragma unroll
+        for (int m = 0; m < 16; m++) {
+            const float2 z = v[brev5(m)];
+            const float2 other = v[brev5(31 - m)];
+            float2 zp;
+            zp.x = __shfl_sync(0xffffffffu, other.x, src_lane);
+            zp.y = __shfl_sync(0xffffffffu, other.y, src_lane);
+            if (lane == 0) zp = (m == 0) ? v[0] : v[brev5(32 - m)];
+            const float2 E = make_float2(z.x + zp.x, z.y - zp.y);
+            const float2 O = make_float2(z.x - zp.x, z.y + zp.y);
+            const float2 T = cmul(O, s_post[m * 32 + lane]);
+            const float2 X = cadd(E, T);
+            const float2 Y = csub(E, T);
+            const float p1 = fmaf(X.x, X.x, X.y * X.y);
+            const float p2 = fmaf(Y.x, Y.x, Y.y * Y.y);
+            const int k = lane + 32 * m;
+            o[k] = finish<MODE>(p1, scale);
+            o[FAST_M - k] = finish<MODE>(p2, scale);
+        }
+        if (lane == 0) {
+            const float2 z = v[brev5(16)];   // bin M/2: X = conj(Z)
+            o[FAST_M / 2] = finish<MODE>(4.0f * fmaf(z.x, z.x, z.y * z.y), scale);
+        }
+        if (++f == n_frames) {
+            f = 0;
+            c++;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Generic path: one CTA per frame, Stockham autosort in shared memory.
+__device__ __forceinline__ void stockham_radix4(const float2 *__restrict__ in,
+                                                float2 *__restrict__ outb,
+                                                const float2 *__restrict__ tw, int M, int Ns,
+                                                int tid, int nthreads) {
+    const int quarter = M >> 2;
+    const int tw_step = M / (Ns * 4);
+    for (int j = tid; j < quarter; j += nthreads) {
+        const int k = j & (Ns - 1);
+        float2 a0 = in[j], a1 = in[j + quarter], a2 = in[j + 2 * quarter],
+               a3 = in[j + 3 * quarter];
+        if (Ns > 1) {
+            a1 = cmul(a1, tw[k * tw_step]);
+            a2 = cmul(a2, tw[2 * k * tw_step]);
+            a3 = cmul(a3, tw[3 * k * tw_step]);
+        }
+        const float2 s02 = cadd(a0, a2), d02 = csub(a0, a2);
+        const float2 s13 = cadd(a1, a3), d13 = mul_mj(csub(a1, a3));
+        const int j0 = ((j - k) << 2) + k;
+        outb[j0] = cadd(s02, s13);
+        outb[j0 + Ns] = cadd(d02, d13);
+        outb[j0 + 2 * Ns] = csub(s02, s13);
+        outb[j0 + 3 * Ns] = csub(d02, d13);
+    }
+}
+
+__global__ void stft_generic_kernel(const float *__restrict__ x, long long x_stride,
+                                    long long n_frames, int hop, float *__restrict__ out,
+                                    long long out_stride_c, long long out_stride_f,
+                                    const float *__restrict__ win,
+                                    const float2 *__restrict__ tw,
+                                    const float2 *__restrict__ post, int mode, int n_fft,
+                                    int log2m) {
+    extern __shared__ float2 smem[];
+    const int M = n_fft >> 1;
+    float2 *buf0 = smem;
+    float2 *buf1 = smem + M;
+    const int tid = threadIdx.x, nthreads = blockDim.x;
+    const long long item = blockIdx.x;
+    const long long c = item / n_frames;
+    const long long f = item - c * n_frames;
+    const float *p = x + c * x_stride + f * hop;
+
+    for (int n = tid; n < M; n += nthreads)
+        buf0[n] = make_float2(__ldg(p + 2 * n) * __ldg(win + 2 * n),
+                              __ldg(p + 2 * n + 1) * __ldg(win + 2 * n + 1));
+    __syncthreads();
+
+    float2 *in = buf0, *ob = buf1;
+    int Ns = 1;
+    if (log2m & 1) {   // one radix-2 pass first (no twiddles at Ns = 1)
+        const int halfm = M >> 1;
+        for (int j = tid; j < halfm; j += nthreads) {
+            const float2 a = in[j], b = in[j + halfm];
+            ob[2 * j] = cadd(a, b);
+            ob[2 * j + 1] = csub(a, b);
+        }
+        __syncthreads();
+        float2 *t = in; in = ob; ob = t;
+        Ns = 2;
+    }
+    for (; Ns < M; Ns <<= 2) {
+        stockham_radix4(in, ob, tw, M, Ns, tid, nthreads);
+        __syncthreads();
+        float2 *t = in; in = ob; ob = t;
+    }
+    // `in` now holds Z[0..M)
+    const float scale = 1.0f / (4.0f * (float)n_fft * (float)n_fft);
+    float *o = out + c * out_stride_c + f * out_stride_f;
+    for (int k = tid; k <= M / 2; k += nthreads) {
+        const float2 z = in[k];
+        const float2 zp = in[(M - k) & (M - 1)];
+        const float2 E = make_float2(z.x + zp.x, z.y - zp.y);
+        const float2 O = make_float2(z.x - zp.x, z.y + zp.y);
+        const float2 T = cmul(O, post[k]);
+        const float2 X = cadd(E, T);
+        const float2 Y = csub(E, T);
+        const float p1 = fmaf(X.x, X.x, X.y * X.y), p2 = fmaf(Y.x, Y.x, Y.y * Y.y);
+        if (mode == FRT_STFT_POWER) {
+            o[k] = finish<FRT_STFT_POWER>(p1, scale);
+            o[M - k] = finish<FRT_STFT_POWER>(p2, scale);
+        } else {
+            o[k] = finish<FRT_STFT_LOGPOWER>(p1, scale);
+            o[M - k] = finish<FRT_STFT_LOGPOWER>(p2, scale);
+        }
+    }
+}
+
+template <int MODE, int VEC>
+cudaError_t set_fast_smem_one() {
+    return cudaFuncSetAttribute(stft2048_kernel<MODE, VEC>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FAST_SMEM);
+}
+cudaError_t set_fast_smem() {
+    cudaError_t e = set_fast_smem_one<0, 0>();
+    if (e == cudaSuccess) e = set_fast_smem_one<0, 1>();
+    if (e == cudaSuccess) e = set_fast_smem_one<1, 0>();
+    if (e == cudaSuccess) e = set_fast_smem_one<1, 1>();
+    return e;
+}
+
+template <int MODE, int VEC>
+void launch_fast(unsigned blocks, cudaStream_t st, const float *x, long long x_stride,
+                 long long n_frames, int hop, float *out, long long osc, long long osf,
+                 const StftPlan &pl, long long total) {
+    stft2048_kernel<MODE, VEC><<<blocks, FAST_WARPS * 32, FAST_SMEM, st>>>(
+        x, x_stride, n_frames, hop, out, osc, osf, reinterpret_cast<const float2 *>(pl.win_dev),
+        pl.tw_dev, pl.post_dev, total);
+}
+
+int ilog2(int v) {
+    int l = 0;
+    while ((1 << l) < v) l++;
+    return l;
+}
+
+}   // namespace
+
+extern "C" int frt_stft_plan(frt_handle h, int n_fft) {
+    if (!h) return FRT_EINVAL;
+    DeviceGuard g(h->device);
+    FRT_CHECK_ARG(h, n_fft >= 32 && n_fft <= 16384 && (n_fft & (n_fft - 1)) == 0,
+                  "n_fft must be a power of two in [32, 16384]");
+    StftPlan &pl = h->stft;
+    if (pl.n_fft == n_fft) return FRT_OK;
+    if (pl.win_dev) cudaFree(pl.win_dev);
+    if (pl.tw_dev) cudaFree(pl.tw_dev);
+    if (pl.post_dev) cudaFree(pl.post_dev);
+    pl = StftPlan();
+    const int N = n_fft, M = N / 2;
+    const double PI = 3.14159265358979323846;
+    // symmetric Hann, friture/audioproc.py:76-81
+    pl.win_host.resize(N);
+    for (int n = 0; n < N; n++)
+        pl.win_host[n] = (float)(0.5 * (1.0 - cos(2.0 * PI * n / (double)(N - 1))));
+    std::vector<float2> tw(M), post(M / 2 + 1 + 32);
+    if (N == FAST_N) {
+        for (int k1 = 0; k1 < 32; k1++)
+            for (int t = 0; t < 32; t++) {
+                const double a = -2.0 * PI * (double)((k1 * t) % M) / (double)M;
+                tw[k1 * 32 + t] = make_float2((float)cos(a), (float)sin(a));
+            }
+    } else {
+        for (int i = 0; i < M; i++) {
+            const double a = -2.0 * PI * (double)i / (double)M;
+            tw[i] = make_float2((float)cos(a), (float)sin(a));
+        }
+    }
+    for (size_t k = 0; k < post.size(); k++) {   // U[k] = -j * W_N^k
+        const double a = 2.0 * PI * (double)k / (double)N;
+        post[k] = make_float2((float)(-sin(a)), (float)(-cos(a)));
+    }
+    FRT_CUDA(h, cudaMalloc(&pl.win_dev, sizeof(float) * N));
+    FRT_CUDA(h, cudaMalloc(&pl.tw_dev, sizeof(float2) * tw.size()));
+    FRT_CUDA(h, cudaMalloc(&pl.post_dev, sizeof(float2) * post.size()));
+    FRT_CUDA(h, cudaMemcpy(pl.win_dev, pl.win_host.data(), sizeof(float) * N,
+                           cudaMemcpyHostToDevice));
+    FRT_CUDA(h, cudaMemcpy(pl.tw_dev, tw.data(), sizeof(float2) * tw.size(),
+                           cudaMemcpyHostToDevice));
+    FRT_CUDA(h, cudaMemcpy(pl.post_dev, post.data(), sizeof(float2) * post.size(),
+                           cudaMemcpyHostToDevice));
+    if (N == FAST_N) {
+        FRT_CUDA(h, set_fast_smem());
+    } else {
+        FRT_CUDA(h, cudaFuncSetAttribute(stft_generic_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(sizeof(float2) * 2 * 8192)));
+    }
+    pl.n_fft = n_fft;
+    return FRT_OK;
+}
+
+extern "C" int frt_stft_window(frt_handle h, float *window_host) {
+    if (!h) return FRT_EINVAL;
+    if (!h->stft.n_fft) return frt_fail(h, FRT_ESTATE, "frt_stft_window: no plan");
+    FRT_CHECK_ARG(h, window_host != nullptr, "window_host is NULL");
+    memcpy(window_host, h->stft.win_host.data(), sizeof(float) * h->stft.n_fft);
+    return FRT_OK;
+}
+
+extern "C" int frt_stft_process(frt_handle h, const float *x_dev, int64_t x_stride,
+                                int n_channels, int64_t n_frames, int hop, float *out_dev,
+                                int64_t out_stride_c, int64_t out_stride_f, int mode,
+                                void *stream) {
+    if (!h) return FRT_EINVAL;
+    DeviceGuard g(h->device);
+    const StftPlan &pl = h->stft;
+    if (!pl.n_fft) return frt_fail(h, FRT_ESTATE, "frt_stft_process: call frt_stft_plan first");
+    FRT_CHECK_ARG(h, n_channels >= 0 && n_frames >= 0, "negative shape");
+    FRT_CHECK_ARG(h, hop >= 1, "hop must be >= 1");
+    FRT_CHECK_ARG(h, mode == FRT_STFT_POWER || mode == FRT_STFT_LOGPOWER, "unknown mode");
+    if (n_channels == 0 || n_frames == 0) return FRT_OK;   // empty input: nothing to do
+    FRT_CHECK_ARG(h, x_dev != nullptr && out_dev != nullptr, "NULL buffer");
+    const int nbins = pl.n_fft / 2 + 1;
+    FRT_CHECK_ARG(h, out_stride_f >= nbins, "out_stride_f smaller than n_fft/2+1");
+    const long long total = (long long)n_channels * n_frames;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (pl.n_fft == FAST_N) {
+        const int vec_ok = (((uintptr_t)x_dev & 7) == 0) && ((x_stride & 1) == 0) &&
+                           ((hop & 1) == 0);
+        long long blocks = (total + FAST_WARPS - 1) / FAST_WARPS;
+        if (blocks > h->sm_count) blocks = h->sm_count;
+#define FRT_LAUNCH_FAST(MODE, VEC)                                                         \
+    launch_fast<MODE, VEC>((unsigned)blocks, st, x_dev, x_stride, n_frames, hop, out_dev,   \
+                           out_stride_c, out_stride_f, pl, total)
+        if (mode == FRT_STFT_POWER) {
+            if (vec_ok) FRT_LAUNCH_FAST(FRT_STFT_POWER, 1);
+            else FRT_LAUNCH_FAST(FRT_STFT_POWER, 0);
+        } else {
+            if (vec_ok) FRT_LAUNCH_FAST(FRT_STFT_LOGPOWER, 1);
+            else FRT_LAUNCH_FAST(FRT_STFT_LOGPOWER, 0);
+        }
+#undef FRT_LAUNCH_FAST
+    } else {
+        FRT_CHECK_ARG(h, total <= 0x7fffffffLL, "too many frames for one launch");
+        const int M = pl.n_fft / 2;
+        int threads = M / 4;
+        if (threads < 32) threads = 32;
+        if (threads > 512) threads = 512;
+        stft_generic_kernel<<<(unsigned)total, threads, sizeof(float2) * 2 * M, st>>>(
+            x_dev, x_stride, n_frames, hop, out_dev, out_stride_c, out_stride_f, pl.win_dev,
+            pl.tw_dev, pl.post_dev, mode, pl.n_fft, ilog2(M));
+    }
+    h->launches++;
+    FRT_CUDA(h, cudaGetLastError());
+    return FRT_OK;
+}
+
+extern "C" int frt_stft_process_host(frt_handle h, const float *x_host, int64_t x_stride,
+                                     int n_channels, int64_t n_samples, int hop,
+                                     float *out_host, int mode) {
+    if (!h) return FRT_EINVAL;
+    DeviceGuard g(h->device);
+    const StftPlan &pl = h->stft;
+    if (!pl.n_fft) return frt_fail(h, FRT_ESTATE, "frt_stft_process_host: no plan");
+    FRT_CHECK_ARG(h, n_channels >= 0 && n_samples >= 0 && hop >= 1, "bad shape");
+    const int N = pl.n_fft, nbins = N / 2 + 1;
+    if (n_channels == 0 || n_samples < N) return FRT_OK;
+    FRT_CHECK_ARG(h, x_host != nullptr && out_host != nullptr, "NULL buffer");
+    FRT_CHECK_ARG(h, x_stride >= n_samples, "x_stride smaller than n_samples");
+    const int64_t frames = (n_samples - N) / hop + 1;
+    // chunk = (channel group) x (frame range), sized to ~32 MiB of output per buffer
+    const size_t budget = (size_t)32 << 20;
+    int64_t fchunk = frames;
+    const size_t out_per_frame = sizeof(float) * nbins;
+    if ((size_t)fchunk * out_per_frame > budget) fchunk = (int64_t)(budget / out_per_frame);
+    if (fchunk < 1) fchunk = 1;
+    int cgroup = 1;
+    if (fchunk == frames) {
+        cgroup = (int)(budget / ((size_t)frames * out_per_frame));
+        if (cgroup < 1) cgroup = 1;
+        if (cgroup > n_channels) cgroup = n_channels;
+    }
+    const int64_t chunk_samples = (fchunk - 1) * (int64_t)hop + N;
+    const size_t in_bytes = sizeof(float) * (size_t)cgroup * chunk_samples;
+    const size_t out_bytes = (size_t)cgroup * fchunk * out_per_frame;
+    int rc = frt_pipe_ensure(h, in_bytes, out_bytes);
+    if (rc) return rc;
+    HostPipe &p = h->pipe;
+    int it = 0;
+    for (int c0 = 0; c0 < n_channels; c0 += cgroup) {
+        const int nc = (c0 + cgroup <= n_channels) ? cgroup : (n_channels - c0);
+        for (int64_t f0 = 0; f0 < frames; f0 += fchunk, it++) {
+            const int64_t nf = (f0 + fchunk <= frames) ? fchunk : (frames - f0);
+            const int64_t ns = (nf - 1) * (int64_t)hop + N;
+            const int b = it & 1;
+            // the H2D may only overwrite d_in[b] after the kernel that read it has finished
+            FRT_CUDA(h, cudaStreamWaitEvent(p.s_in, p.ev_cmp[b], 0));
+            FRT_CUDA(h, cudaMemcpy2DAsync(p.d_in[b], sizeof(float) * ns,
+                                          x_host + (size_t)c0 * x_stride + f0 * hop,
+                                          sizeof(float) * x_stride, sizeof(float) * ns, nc,
+                                          cudaMemcpyHostToDevice, p.s_in));
+            FRT_CUDA(h, cudaEventRecord(p.ev_in[b], p.s_in));
+            FRT_CUDA(h, cudaStreamWaitEvent(p.s_cmp, p.ev_in[b], 0));
+            FRT_CUDA(h, cudaStreamWaitEvent(p.s_cmp, p.ev_out[b], 0));   // d_out[b] drained
+            rc = frt_stft_process(h, p.d_in[b], ns, nc, nf, hop, p.d_out[b],
+                                  nf * (int64_t)nbins, nbins, mode, p.s_cmp);
+            if (rc) return rc;
+            FRT_CUDA(h, cudaEventRecord(p.ev_cmp[b], p.s_cmp));
+            FRT_CUDA(h, cudaStreamWaitEvent(p.s_out, p.ev_cmp[b], 0));
+            FRT_CUDA(h, cudaMemcpy2DAsync(out_host + ((size_t)c0 * frames + f0) * nbins,
+                                          sizeof(float) * frames * nbins, p.d_out[b],
+                                          sizeof(float) * nf * nbins,
+                                          sizeof(float) * nf * nbins, nc,
+                                          cudaMemcpyDeviceToHost, p.s_out));
+            FRT_CUDA(h, cudaEventRecord(p.ev_out[b], p.s_out));
+        }
+    }
+    FRT_CUDA(h, cudaStreamSynchronize(p.s_out));
+    FRT_CUDA(h, cudaStreamSynchronize(p.s_cmp));
+    FRT_CUDA(h, cudaStreamSynchronize(p.s_in));
+    return FRT_OK;
+}

@@ -1,0 +1,66 @@
+"""Parity metrics shared by the GPU tests, the CPU tests and bench.py's parity gate.
+
+north_star: outputs match the reference "within 1e-5 relative float32 on the log-power and
+band-energy vectors".  The relative error of a vector is max|got-ref| / max(max|ref|, 1)
+(SURVEY.md 8d).
+
+float32 arithmetic has an amplitude noise floor: a 2048-point float32 FFT carries an absolute
+error of about 2e-7 x (rms spectral amplitude of the frame) in every bin, whatever the bin's
+own level.  On the dB scale this is invisible for ordinary bins and unbounded for deep nulls
+(|X| -> 0), which occur with probability ~1e-5 per bin at -50 dB below the frame's mean power
+for broadband input.  The log-power criterion is therefore applied as is to bins no more than
+FLOOR_DB below the frame's mean power; every bin, nulls included, must stay within
+TOL*max|ref| + 20*log10(1 + AMP_TOL*rms/|X_ref|), i.e. the same tolerance widened by the dB
+image of an amplitude error of AMP_TOL x (frame rms) -- about 10x the float32 FFT noise floor.
+"""
+import numpy as np
+
+TOL = 1e-5        # relative error of the log-power / band-energy vector
+FLOOR_DB = 50.0   # log-power criterion applies down to this far below the frame's mean power
+AMP_TOL = 2e-6    # amplitude noise allowance for deep nulls, relative to the frame rms
+
+
+def rel_err(got, ref):
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    if got.size == 0:
+        return 0.0
+    return float(np.max(np.abs(got - ref)) / max(np.max(np.abs(ref)), 1.0))
+
+
+def logpower_errors(got_db, ref_db, eps=1e-30):
+    """got_db, ref_db: [..., bins] log-power (10*log10(P+eps)).  Returns a dict with
+    rel_above_floor (vector-relative error over bins >= mean-FLOOR_DB), amp_err (worst
+    amplitude error over ALL bins, relative to the frame rms), rel_all, frac_above_floor."""
+    got_db = np.asarray(got_db, dtype=np.float64)
+    ref_db = np.asarray(ref_db, dtype=np.float64)
+    p_ref = np.maximum(10.0 ** (ref_db / 10.0) - eps, 0.0)
+    mean_p = np.mean(p_ref, axis=-1, keepdims=True)
+    floor_db = 10.0 * np.log10(mean_p + eps) - FLOOR_DB
+    mask = ref_db >= floor_db
+    denom = max(float(np.max(np.abs(ref_db))), 1.0) if ref_db.size else 1.0
+    diff = np.abs(got_db - ref_db)
+    rms = np.sqrt(mean_p)
+    amp_ref = np.sqrt(p_ref)
+    noise_db = 20.0 * np.log10(1.0 + AMP_TOL * rms / np.maximum(amp_ref, 1e-300))
+    noise_db = np.where(rms > 0, noise_db, 0.0)
+    allowed = TOL * denom + noise_db
+    return {
+        "rel_above_floor": float(np.max(diff[mask]) / denom) if mask.any() else 0.0,
+        "rel_all": float(np.max(diff) / denom) if diff.size else 0.0,
+        "worst_ratio_all": float(np.max(diff / allowed)) if diff.size else 0.0,
+        "frac_above_floor": float(np.mean(mask)) if mask.size else 1.0,
+    }
+
+
+def logpower_ok(e, min_frac=0.999):
+    return (e["rel_above_floor"] < TOL and e["worst_ratio_all"] < 1.0
+            and e["frac_above_floor"] >= min_frac)
+
+
+def assert_logpower_parity(got_db, ref_db, min_frac=0.999):
+    """min_frac: broadband inputs must have (almost) every bin above the floor; tonal inputs,
+    whose mean power is dominated by a few bins, pass min_frac=0."""
+    e = logpower_errors(got_db, ref_db)
+    assert logpower_ok(e, min_frac), e
+    return e
