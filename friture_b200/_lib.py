@@ -53,6 +53,13 @@ SIGNATURES = {
                                  c_int64, c_int64, c_int, c_void_p]),
     "frt_stft_process_host": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int64, c_int,
                                       c_void_p, c_int]),
+    "frt_bank_plan": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "frt_bank_reset": (c_int, [c_void_p]),
+    "frt_bank_process": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p,
+                                 c_int64, c_int, c_void_p]),
+    "frt_bank_state_size": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64)]),
+    "frt_bank_get_state": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "frt_bank_set_state": (c_int, [c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None

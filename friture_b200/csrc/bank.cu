@@ -1,2 +1,541 @@
+// Multi-rate fractional-octave IIR filterbank + exponential RMS for sm_100a.
+//
+// Stands behind Octave_Filters.filter (friture/octavefilters.py:49-58) with the numerics of the
+// reference's IIR bank octave_filter_bank_decimation (friture/filter.py:86-118: per stage j,
+// bands bpo-1..0 filter x_j, then x_{j+1} = lowpass(x_j)[::2], friture/signal/decimate.py:39-41),
+// and behind the widget's per-band smoothing exp_smoothed_value(y**2)
+// (friture/octavespectrum.py:104, friture/signal/exp_smoothing.py:11-56).  The (b, a) filters of
+// friture/generated_filters.py are run as float32 second-order sections (direct form II
+// transposed, the recursion of friture/signal/lfilter.py:131-139 per section).
+//
+// ONE WARP PER CHANNEL.  An IIR recursion is serial in time, so the time axis of a tile of
+// 32*L0 samples is split over the 32 lanes (lane l owns samples [l*L, (l+1)*L) of the stage's
+// signal, in registers) and every biquad section is run as
+//   pass 1  zero-state recursion over the lane's chunk -> local final state f_l
+//   scan    s_l = A^L s_{l-1} + f_l over the lanes (5 shuffle steps with A^(L*2^k), 2x2)
+//   pass 2  the recursion again from the true incoming state -> outputs, in place.
+// The decimated output stays in the same lane (L halves each stage).  Once a stage has only
+// 32 samples left per tile (one per lane) the remaining low-rate stages switch to
+// "lane = filter chain": lanes 0..bpo-1 run the band chains and lane bpo the decimator chain
+// serially over the <=32 samples, which are broadcast with shuffles.
+// Filter and smoothing state lives in shared memory while the kernel runs (global in between).
+#include <cmath>
+
 #include "frt_internal.cuh"
-void frt_bank_release(frt_ctx *) {}
+
+namespace {
+
+constexpr int MAX_BPO = 24;
+constexpr int MAX_SEC = 2 * MAX_BPO + 6;
+constexpr int MAX_OCT = 10;
+constexpr int NQ = 10;   // A^(2^q), q = 0..9: chunk L <= 32 (q <= 5) plus 4 doublings
+
+struct BankParams {
+    float coef[MAX_SEC][8];        // b0 b1 b2 a1 a2 B1 B2 -, B = (b1 - a1 b0, b2 - a2 b0)
+    float apow[MAX_SEC][NQ][4];    // A^(2^q), A = [[-a1, 1], [-a2, 0]], row-major
+    float qpow[MAX_OCT][NQ];       // (1 - alpha_j)^(2^q)
+    float alpha[MAX_OCT];
+    int bpo, n_oct, nsec;          // nsec = 2*bpo + 6; band i section s -> 2*i+s; dec s -> 2*bpo+s
+};
+
+struct BankArgs {
+    const float *x;
+    long long x_stride;
+    int n_channels;
+    int n_tiles;           // tiles per launch (per channel)
+    int tiles_per_block;   // energies are emitted after every tiles_per_block-th tile
+    float *zstate;         // [C][n_oct][nsec][2]
+    float *ema;            // [C][n_oct][bpo]   smoothed energies / alpha_j (dispbuffers / alpha)
+    float *energies;       // [C][n_blocks][nbands] or NULL
+    float *y;              // ragged band outputs or NULL
+    long long y_stride;
+    long long t_total;     // samples per channel in this launch (n_tiles * tile)
+    int db;                // 1: energies as 10*log10(e + 1e-30)
+    int vec_ok;
+};
+
+__device__ __forceinline__ float lg2_fast(float v) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+
+__device__ __forceinline__ float energy_out(float e, int db) {
+    // friture/octavespectrum.py:119-120: 10*log10(sp + 1e-30)
+    return db ? 3.01029995663981195f * lg2_fast(e + 1e-30f) : e;
+}
+
+// offset of band k in the ragged per-channel y layout (bands concatenated, k = 0 lowest)
+__device__ __forceinline__ long long y_offset(int k, int bpo, int n_oct, long long t_total) {
+    // bands of stage j (dec 2^j) are k = (n_oct-1-j)*bpo + i; lower k = higher j = shorter
+    const int jk = n_oct - 1 - k / bpo;        // stage of band k
+    const int i = k - (n_oct - 1 - jk) * bpo;
+    // sum over stages j' > jk of bpo * (T >> j')  +  i * (T >> jk)
+    long long off = 0;
+    for (int j = n_oct - 1; j > jk; j--) off += (long long)bpo * (t_total >> j);
+    return off + (long long)i * (t_total >> jk);
+}
+
+struct WarpCtx {
+    const BankParams *P;
+    float *s_z;       // [n_oct][nsec][2]   this warp's filter state (shared memory)
+    float *s_e;       // [n_oct][bpo]       this warp's smoothing state (e / alpha form)
+    const float *s_coef;   // [nsec][8] CTA copy of the coefficients for lane-varying access
+    float *energies;  // this channel, this block: [nbands] or NULL when not a block end
+    float *y;         // this channel's ragged y base or NULL
+    long long t_total;
+    long long t_off;  // sample offset of this tile within the launch
+    int lane;
+    int db;
+};
+
+// ---------------------------------------------------------------- scan-mode section
+template <int L> struct Log2 { static constexpr int v = 1 + Log2<L / 2>::v; };
+template <> struct Log2<1> { static constexpr int v = 0; };
+
+template <int L>
+__device__ __forceinline__ void section_scan(const float (&in)[L], float (&out)[L],
+                                             const WarpCtx &w, int j, int sec) {
+    const BankParams &P = *w.P;
+    const float b0 = P.coef[sec][0], b1 = P.coef[sec][1], b2 = P.coef[sec][2];
+    const float a1 = P.coef[sec][3], a2 = P.coef[sec][4];
+    const float B1 = P.coef[sec][5], B2 = P.coef[sec][6];
+    float *zp = w.s_z + (j * P.nsec + sec) * 2;
+    const float c1 = zp[0], c2 = zp[1];
+    // pass 1: state-only recursion from zero state
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < L; k++) {
+        const float x = in[k];
+        const float n1 = fmaf(-a1, s1, fmaf(B1, x, s2));
+        s2 = fmaf(-a2, s1, B2 * x);
+        s1 = n1;
+    }
+    constexpr int q0 = Log2<L>::v;
+    if (w.lane == 0) {   // fold the carried state into lane 0's segment
+        const float *A = P.apow[sec][q0];
+        s1 += fmaf(A[0], c1, A[1] * c2);
+        s2 += fmaf(A[2], c1, A[3] * c2);
+    }
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        const float *A = P.apow[sec][q0 + k];
+        const float t1 = __shfl_up_sync(0xffffffffu, s1, 1 << k);
+        const float t2 = __shfl_up_sync(0xffffffffu, s2, 1 << k);
+        if (w.lane >= (1 << k)) {
+            s1 = fmaf(A[0], t1, fmaf(A[1], t2, s1));
+            s2 = fmaf(A[2], t1, fmaf(A[3], t2, s2));
+        }
+    }
+    float i1 = __shfl_up_sync(0xffffffffu, s1, 1);
+    float i2 = __shfl_up_sync(0xffffffffu, s2, 1);
+    if (w.lane == 0) {
+        i1 = c1;
+        i2 = c2;
+    }
+    // pass 2: direct form II transposed (friture/signal/lfilter.py:131-139, order 2)
+#pragma unroll
+    for (int k = 0; k < L; k++) {
+        const float x = in[k];
+        const float y = fmaf(b0, x, i1);
+        i1 = fmaf(-a1, y, fmaf(b1, x, i2));
+        i2 = fmaf(-a2, y, b2 * x);
+        out[k] = y;
+    }
+    __syncwarp();
+    if (w.lane == 31) {   // state after the tile's last sample
+        zp[0] = i1;
+        zp[1] = i2;
+    }
+}
+
+template <int N> __device__ void serial_stage(float xin, const WarpCtx &w, int j);
+
+// One scan-mode stage: L samples per lane, 32 lanes active.
+template <int L>
+__device__ void scan_stage(const float (&xc)[L], const WarpCtx &w, int j) {
+    const BankParams &P = *w.P;
+    const int bpo = P.bpo;
+    float wk[L];
+    // bands bpo-1 .. 0 (friture/filter.py:105)
+    for (int i = bpo - 1; i >= 0; i--) {
+        section_scan<L>(xc, wk, w, j, 2 * i);
+        section_scan<L>(wk, wk, w, j, 2 * i + 1);
+        const int kband = (P.n_oct - 1 - j) * bpo + i;
+        if (w.y) {
+            float *yp = w.y + y_offset(kband, bpo, P.n_oct, w.t_total) + (w.t_off >> j) +
+                        w.lane * L;
+#pragma unroll
+            for (int k = 0; k < L; k++) yp[k] = wk[k];
+        }
+        // exponential smoothing of y^2 (friture/signal/exp_smoothing.py:11-56), e/alpha form
+        const float q = P.qpow[j][0];
+        float e = 0.f;
+#pragma unroll
+        for (int k = 0; k < L; k++) e = fmaf(e, q, wk[k] * wk[k]);
+        float *ep = w.s_e + j * bpo + i;
+        constexpr int q0 = Log2<L>::v;
+        if (w.lane == 0) e = fmaf(P.qpow[j][q0], ep[0], e);
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            const float t = __shfl_up_sync(0xffffffffu, e, 1 << k);
+            if (w.lane >= (1 << k)) e = fmaf(P.qpow[j][q0 + k], t, e);
+        }
+        __syncwarp();
+        if (w.lane == 31) {
+            ep[0] = e;
+            if (w.energies) w.energies[kband] = energy_out(P.alpha[j] * e, w.db);
+        }
+    }
+    if (j + 1 >= P.n_oct) return;   // the last decimator's output is discarded (filter.py:113)
+    // decimator: 6 sections, then keep even samples (friture/signal/decimate.py:39-41)
+    section_scan<L>(xc, wk, w, j, 2 * bpo);
+#pragma unroll 1
+    for (int s = 1; s < 6; s++) section_scan<L>(wk, wk, w, j, 2 * bpo + s);
+    if constexpr (L >= 4) {
+        float xn[L / 2];
+#pragma unroll
+        for (int k = 0; k < L / 2; k++) xn[k] = wk[2 * k];
+        scan_stage<L / 2>(xn, w, j + 1);
+    } else {
+        // L == 2: one sample per lane is left -> switch to lane = chain
+        serial_stage<32>(wk[0], w, j + 1);
+    }
+}
+
+// Serial-mode stage: N samples, sample m in lane m.  Lane r < bpo runs band chain r (2
+// sections), lane bpo runs the decimator chain (6 sections).
+template <int N>
+__device__ void serial_stage(float xin, const WarpCtx &w, int j) {
+    const BankParams &P = *w.P;
+    const int bpo = P.bpo, lane = w.lane;
+    const bool last = (j + 1 >= P.n_oct);
+    const bool is_band = lane < bpo;
+    const bool is_dec = (lane == bpo) && !last;
+    const int nchain = is_band ? 2 : (is_dec ? 6 : 0);
+    const int sec0 = is_band ? 2 * lane : 2 * bpo;
+    const int nloop = last ? 2 : 6;
+    float z1[6], z2[6], cb0[6], cb1[6], cb2[6], ca1[6], ca2[6];
+#pragma unroll
+    for (int s = 0; s < 6; s++) {
+        const bool on = s < nchain;
+        const float *cf = w.s_coef + (sec0 + (on ? s : 0)) * 8;
+        cb0[s] = cf[0]; cb1[s] = cf[1]; cb2[s] = cf[2]; ca1[s] = cf[3]; ca2[s] = cf[4];
+        const float *zp = w.s_z + (j * P.nsec + sec0 + (on ? s : 0)) * 2;
+        z1[s] = zp[0];
+        z2[s] = zp[1];
+    }
+    const float q = P.qpow[j][0];
+    float e = is_band ? w.s_e[j * bpo + lane] : 0.f;
+    const int kband = (P.n_oct - 1 - j) * bpo + (is_band ? lane : 0);
+    float *yp = nullptr;
+    if (w.y && is_band)
+        yp = w.y + y_offset(kband, bpo, P.n_oct, w.t_total) + (w.t_off >> j);
+    float xnext = 0.f;
+#pragma unroll
+    for (int m = 0; m < N; m++) {
+        float v = __shfl_sync(0xffffffffu, xin, m);
+#pragma unroll
+        for (int s = 0; s < 6; s++) {
+            if (s < nloop && s < nchain) {
+                const float y = fmaf(cb0[s], v, z1[s]);
+                z1[s] = fmaf(-ca1[s], y, fmaf(cb1[s], v, z2[s]));
+                z2[s] = fmaf(-ca2[s], y, cb2[s] * v);
+                v = y;
+            }
+        }
+        if (is_band) {
+            e = fmaf(e, q, v * v);
+            if (yp) yp[m] = v;
+        }
+        if (!last && (m & 1) == 0) {
+            const float o = __shfl_sync(0xffffffffu, v, bpo);
+            if (lane == (m >> 1)) xnext = o;
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int s = 0; s < 6; s++) {
+        if (s < nchain) {
+            float *zp = w.s_z + (j * P.nsec + sec0 + s) * 2;
+            zp[0] = z1[s];
+            zp[1] = z2[s];
+        }
+    }
+    if (is_band) {
+        w.s_e[j * bpo + lane] = e;
+        if (w.energies) w.energies[kband] = energy_out(P.alpha[j] * e, w.db);
+    }
+    __syncwarp();
+    if constexpr (N >= 2) {
+        if (!last) serial_stage<N / 2>(xnext, w, j + 1);
+    }
+}
+
+template <int L0>
+__global__ void __launch_bounds__(64)
+bank_kernel(const __grid_constant__ BankParams P, const BankArgs a) {
+    extern __shared__ float smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int warps = blockDim.x >> 5;
+    const int nz = P.n_oct * P.nsec * 2, ne = P.n_oct * P.bpo;
+    float *s_coef = smem;                        // [nsec][8]
+    float *s_z = s_coef + P.nsec * 8 + wid * (nz + ne);
+    float *s_e = s_z + nz;
+    for (int i = threadIdx.x; i < P.nsec * 8; i += blockDim.x)
+        s_coef[i] = P.coef[i >> 3][i & 7];
+    const int c = blockIdx.x * warps + wid;
+    const bool active = c < a.n_channels;
+    if (active) {
+        const float *gz = a.zstate + (size_t)c * nz;
+        const float *ge = a.ema + (size_t)c * ne;
+        for (int i = lane; i < nz; i += 32) s_z[i] = gz[i];
+        for (int i = lane; i < ne; i += 32) s_e[i] = ge[i];   // e/alpha form: e = q e + y^2
+    }
+    __syncthreads();
+    if (!active) return;
+
+    constexpr int TILE = 32 * L0;
+    const int nbands = P.n_oct * P.bpo;
+    WarpCtx w;
+    w.P = &P;
+    w.s_z = s_z;
+    w.s_e = s_e;
+    w.s_coef = s_coef;
+    w.lane = lane;
+    w.db = a.db;
+    w.t_total = a.t_total;
+    w.y = a.y ? a.y + (size_t)c * a.y_stride : nullptr;
+    const float *xch = a.x + (size_t)c * a.x_stride;
+    const int n_blocks = a.n_tiles / a.tiles_per_block;
+    for (int t = 0; t < a.n_tiles; t++) {
+        const float *xp = xch + (size_t)t * TILE + lane * L0;
+        float xc[L0];
+        if (a.vec_ok) {
+#pragma unroll
+            for (int k = 0; k < L0; k += 4) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(xp + k));
+                xc[k] = v.x; xc[k + 1] = v.y; xc[k + 2] = v.z; xc[k + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < L0; k++) xc[k] = __ldg(xp + k);
+        }
+        const bool block_end = ((t + 1) % a.tiles_per_block) == 0;
+        w.energies = (a.energies && block_end)
+                         ? a.energies + ((size_t)c * n_blocks + t / a.tiles_per_block) * nbands
+                         : nullptr;
+        w.t_off = (long long)t * TILE;
+        scan_stage<L0>(xc, w, 0);
+        __syncwarp();
+    }
+    // write the state back
+    float *gz = a.zstate + (size_t)c * nz;
+    float *ge = a.ema + (size_t)c * ne;
+    for (int i = lane; i < nz; i += 32) gz[i] = s_z[i];
+    for (int i = lane; i < ne; i += 32) ge[i] = s_e[i];
+}
+
+}   // namespace
+
+struct BankPlan {
+    BankParams params;
+    int n_channels = 0;
+    float *zstate = nullptr;
+    float *ema = nullptr;
+    size_t nz = 0, ne = 0;   // floats per channel
+};
+
+void frt_bank_release(frt_ctx *h) {
+    if (!h->bank) return;
+    if (h->bank->zstate) cudaFree(h->bank->zstate);
+    if (h->bank->ema) cudaFree(h->bank->ema);
+    delete h->bank;
+    h->bank = nullptr;
+}
+
+static void mat2_mul(const double a[4], const double b[4], double o[4]) {
+    o[0] = a[0] * b[0] + a[1] * b[2];
+    o[1] = a[0] * b[1] + a[1] * b[3];
+    o[2] = a[2] * b[0] + a[3] * b[2];
+    o[3] = a[2] * b[1] + a[3] * b[3];
+}
+
+extern "C" int frt_bank_plan(frt_handle h, int n_channels, int bands_per_octave, int n_octaves,
+                             const double *sos_band, const double *sos_dec,
+                             const double *alphas) {
+    if (!h) return FRT_EINVAL;
+    DeviceGuard g(h->device);
+    FRT_CHECK_ARG(h, n_channels >= 1, "n_channels must be >= 1");
+    FRT_CHECK_ARG(h, bands_per_octave >= 1 && bands_per_octave <= MAX_BPO,
+                  "bands_per_octave must be in [1, 24]");
+    FRT_CHECK_ARG(h, n_octaves >= 1 && n_octaves <= MAX_OCT, "n_octaves must be in [1, 10]");
+    FRT_CHECK_ARG(h, sos_band && sos_dec && alphas, "NULL coefficient table");
+    frt_bank_release(h);
+    BankPlan *pl = new (std::nothrow) BankPlan();
+    if (!pl) return frt_fail(h, FRT_ENOMEM, "out of host memory");
+    BankParams &P = pl->params;
+    memset(&P, 0, sizeof(P));
+    P.bpo = bands_per_octave;
+    P.n_oct = n_octaves;
+    P.nsec = 2 * bands_per_octave + 6;
+    for (int sec = 0; sec < P.nsec; sec++) {
+        const double *s = sec < 2 * bands_per_octave ? sos_band + (size_t)sec * 6
+                                                     : sos_dec + (size_t)(sec - 2 * bands_per_octave) * 6;
+        if (fabs(s[3] - 1.0) > 1e-12) {
+            delete pl;
+            return frt_fail(h, FRT_EINVAL, "SOS section %d has a0 != 1", sec);
+        }
+        const double b0 = s[0], b1 = s[1], b2 = s[2], a1 = s[4], a2 = s[5];
+        P.coef[sec][0] = (float)b0; P.coef[sec][1] = (float)b1; P.coef[sec][2] = (float)b2;
+        P.coef[sec][3] = (float)a1; P.coef[sec][4] = (float)a2;
+        // the scan must propagate the state of the float32 filter that pass 2 runs
+        const double fb0 = P.coef[sec][0], fb1 = P.coef[sec][1], fb2 = P.coef[sec][2];
+        const double fa1 = P.coef[sec][3], fa2 = P.coef[sec][4];
+        P.coef[sec][5] = (float)(fb1 - fa1 * fb0);
+        P.coef[sec][6] = (float)(fb2 - fa2 * fb0);
+        double A[4] = {-fa1, 1.0, -fa2, 0.0};
+        for (int q = 0; q < NQ; q++) {
+            for (int i = 0; i < 4; i++) P.apow[sec][q][i] = (float)A[i];
+            double A2[4];
+            mat2_mul(A, A, A2);
+            memcpy(A, A2, sizeof(A));
+        }
+    }
+    for (int j = 0; j < n_octaves; j++) {
+        if (!(alphas[j] > 0.0 && alphas[j] <= 1.0)) {
+            delete pl;
+            return frt_fail(h, FRT_EINVAL, "alpha[%d] must be in (0, 1]", j);
+        }
+        P.alpha[j] = (float)alphas[j];
+        double q = 1.0 - alphas[j];
+        for (int k = 0; k < NQ; k++) {
+            P.qpow[j][k] = (float)q;
+            q *= q;
+        }
+    }
+    pl->n_channels = n_channels;
+    pl->nz = (size_t)n_octaves * P.nsec * 2;
+    pl->ne = (size_t)n_octaves * bands_per_octave;
+    cudaError_t e = cudaMalloc(&pl->zstate, sizeof(float) * pl->nz * n_channels);
+    if (e == cudaSuccess) e = cudaMalloc(&pl->ema, sizeof(float) * pl->ne * n_channels);
+    if (e == cudaSuccess) e = cudaMemset(pl->zstate, 0, sizeof(float) * pl->nz * n_channels);
+    if (e == cudaSuccess) e = cudaMemset(pl->ema, 0, sizeof(float) * pl->ne * n_channels);
+    if (e != cudaSuccess) {
+        if (pl->zstate) cudaFree(pl->zstate);
+        if (pl->ema) cudaFree(pl->ema);
+        delete pl;
+        return frt_fail(h, FRT_ECUDA, "frt_bank_plan: %s", cudaGetErrorString(e));
+    }
+    h->bank = pl;
+    return FRT_OK;
+}
+
+extern "C" int frt_bank_reset(frt_handle h) {
+    if (!h) return FRT_EINVAL;
+    if (!h->bank) return frt_fail(h, FRT_ESTATE, "frt_bank_reset: no plan");
+    DeviceGuard g(h->device);
+    BankPlan *pl = h->bank;
+    FRT_CUDA(h, cudaMemset(pl->zstate, 0, sizeof(float) * pl->nz * pl->n_channels));
+    FRT_CUDA(h, cudaMemset(pl->ema, 0, sizeof(float) * pl->ne * pl->n_channels));
+    return FRT_OK;
+}
+
+extern "C" int frt_bank_state_size(frt_handle h, int64_t *z_floats, int64_t *ema_floats) {
+    if (!h) return FRT_EINVAL;
+    if (!h->bank) return frt_fail(h, FRT_ESTATE, "frt_bank_state_size: no plan");
+    if (z_floats) *z_floats = (int64_t)(h->bank->nz * h->bank->n_channels);
+    if (ema_floats) *ema_floats = (int64_t)(h->bank->ne * h->bank->n_channels);
+    return FRT_OK;
+}
+
+extern "C" int frt_bank_get_state(frt_handle h, float *z_host, float *ema_host) {
+    if (!h) return FRT_EINVAL;
+    if (!h->bank) return frt_fail(h, FRT_ESTATE, "frt_bank_get_state: no plan");
+    DeviceGuard g(h->device);
+    BankPlan *pl = h->bank;
+    FRT_CUDA(h, cudaDeviceSynchronize());
+    if (z_host)
+        FRT_CUDA(h, cudaMemcpy(z_host, pl->zstate, sizeof(float) * pl->nz * pl->n_channels,
+                               cudaMemcpyDeviceToHost));
+    if (ema_host)
+        FRT_CUDA(h, cudaMemcpy(ema_host, pl->ema, sizeof(float) * pl->ne * pl->n_channels,
+                               cudaMemcpyDeviceToHost));
+    return FRT_OK;
+}
+
+extern "C" int frt_bank_set_state(frt_handle h, const float *z_host, const float *ema_host) {
+    if (!h) return FRT_EINVAL;
+    if (!h->bank) return frt_fail(h, FRT_ESTATE, "frt_bank_set_state: no plan");
+    DeviceGuard g(h->device);
+    BankPlan *pl = h->bank;
+    FRT_CUDA(h, cudaDeviceSynchronize());
+    if (z_host)
+        FRT_CUDA(h, cudaMemcpy(pl->zstate, z_host, sizeof(float) * pl->nz * pl->n_channels,
+                               cudaMemcpyHostToDevice));
+    if (ema_host)
+        FRT_CUDA(h, cudaMemcpy(pl->ema, ema_host, sizeof(float) * pl->ne * pl->n_channels,
+                               cudaMemcpyHostToDevice));
+    return FRT_OK;
+}
+
+template <int L0>
+static cudaError_t launch_bank(const BankPlan *pl, const BankArgs &a, cudaStream_t st) {
+    const BankParams &P = pl->params;
+    const int warps = 2;
+    const size_t smem = sizeof(float) * ((size_t)P.nsec * 8 + (size_t)warps * (pl->nz + pl->ne));
+    cudaError_t e = cudaFuncSetAttribute(bank_kernel<L0>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const unsigned blocks = (unsigned)((a.n_channels + warps - 1) / warps);
+    bank_kernel<L0><<<blocks, warps * 32, smem, st>>>(P, a);
+    return cudaGetLastError();
+}
+
+extern "C" int frt_bank_process(frt_handle h, const float *x_dev, int64_t x_stride, int block,
+                                int n_blocks, float *energies_dev, float *y_dev,
+                                int64_t y_stride, int db, void *stream) {
+    if (!h) return FRT_EINVAL;
+    if (!h->bank) return frt_fail(h, FRT_ESTATE, "frt_bank_process: call frt_bank_plan first");
+    DeviceGuard g(h->device);
+    BankPlan *pl = h->bank;
+    const BankParams &P = pl->params;
+    FRT_CHECK_ARG(h, n_blocks >= 0 && block >= 0, "negative shape");
+    if (n_blocks == 0 || block == 0) return FRT_OK;   // empty chunk: octavespectrum.py:94-95
+    // blocks must stay even-length at every stage (decimate.py:41 restarts the [::2] phase
+    // on every call), i.e. block % 2^(n_oct-1) == 0; the kernel tiles are 256/512/1024
+    FRT_CHECK_ARG(h, block % 256 == 0, "block must be a multiple of 256 samples");
+    FRT_CHECK_ARG(h, x_dev != nullptr, "x_dev is NULL");
+    FRT_CHECK_ARG(h, x_stride >= (int64_t)block * n_blocks, "x_stride too small");
+    int tile = (block % 1024 == 0) ? 1024 : ((block % 512 == 0) ? 512 : 256);
+    FRT_CHECK_ARG(h, (tile >> (P.n_oct - 1)) >= 1, "block too short for this many octaves");
+    const long long t_total = (long long)block * n_blocks;
+    if (y_dev) {
+        long long need = 0;
+        for (int j = 0; j < P.n_oct; j++) need += (long long)P.bpo * (t_total >> j);
+        FRT_CHECK_ARG(h, y_stride >= need, "y_stride smaller than the ragged output size");
+    }
+    BankArgs a;
+    a.x = x_dev;
+    a.x_stride = x_stride;
+    a.n_channels = pl->n_channels;
+    a.n_tiles = (int)(t_total / tile);
+    a.tiles_per_block = block / tile;
+    a.zstate = pl->zstate;
+    a.ema = pl->ema;
+    a.energies = energies_dev;
+    a.y = y_dev;
+    a.y_stride = y_stride;
+    a.t_total = t_total;
+    a.db = db;
+    a.vec_ok = (((uintptr_t)x_dev & 15) == 0) && ((x_stride & 3) == 0);
+    cudaError_t e;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (tile == 1024) e = launch_bank<32>(pl, a, st);
+    else if (tile == 512) e = launch_bank<16>(pl, a, st);
+    else e = launch_bank<8>(pl, a, st);
+    h->launches++;
+    if (e != cudaSuccess)
+        return frt_fail(h, FRT_ECUDA, "bank kernel launch: %s", cudaGetErrorString(e));
+    return FRT_OK;
+}

@@ -74,6 +74,43 @@ int frt_stft_process(frt_handle h, const float *x_dev, int64_t x_stride, int n_c
 int frt_stft_process_host(frt_handle h, const float *x_host, int64_t x_stride, int n_channels,
                           int64_t n_samples, int hop, float *out_host, int mode);
 
+/* ---------------------------------------------------------------- filterbank (Octave_Filters)
+ * Stands behind friture/octavefilters.py:37-158 (`Octave_Filters.filter`, `setbandsperoctave`)
+ * with the numerics of the reference's IIR bank `octave_filter_bank_decimation`
+ * (friture/filter.py:86-118, `decimate` friture/signal/decimate.py:27-42, recursion
+ * friture/signal/lfilter.py:85-147), fused with the octave widget's smoothing
+ * `exp_smoothed_value(kernel, alpha, y**2, old)` (friture/octavespectrum.py:104,140-156;
+ * friture/signal/exp_smoothing.py:11-56) and `10*log10(sp+1e-30)` (octavespectrum.py:119-120). */
+
+/* Build the filterbank for `n_channels` independent streams.
+ *   sos_band  [bands_per_octave][2][6]  second-order sections (b0 b1 b2 1 a1 a2) of the
+ *             band-passes of the top octave, band 0 = lowest (generated_filters.PARAMS[bpo])
+ *   sos_dec   [6][6]                    sections of the decimation low-pass (PARAMS['dec'])
+ *   alphas    [n_octaves]               smoothing factor per stage j (rate fs/2^j),
+ *             octavespectrum.py:150-154
+ * Filter and smoothing state start at zero (filter.py:121-133; octavespectrum.py:59).        */
+int frt_bank_plan(frt_handle h, int n_channels, int bands_per_octave, int n_octaves,
+                  const double *sos_band, const double *sos_dec, const double *alphas);
+int frt_bank_reset(frt_handle h);
+/* Process n_blocks consecutive blocks of `block` samples per channel
+ * (x[c*x_stride + b*block + n]); block % 256 == 0 (the reference needs even lengths at every
+ * stage, decimate.py:41).  State is carried across calls, so any blocking of a stream gives
+ * the same result.
+ *   energies_dev  [C][n_blocks][nbands] or NULL: smoothed band energies after each block
+ *                 (band k = (n_octaves-1-j)*bpo + i as in filter.py:104-109); dB when db != 0
+ *   y_dev         NULL, or the band outputs themselves (the literal `.filter()` contract):
+ *                 channel c at y_dev + c*y_stride, bands concatenated k = 0..nbands-1, band k
+ *                 holding (block*n_blocks) >> j samples                                       */
+int frt_bank_process(frt_handle h, const float *x_dev, int64_t x_stride, int block, int n_blocks,
+                     float *energies_dev, float *y_dev, int64_t y_stride, int db, void *stream);
+/* State checkpoint / resume (the reference keeps its state inside the object,
+ * octavefilters.py:50-56).  z: [C][n_octaves][2*bpo+6][2] section states; ema:
+ * [C][n_octaves][bpo] smoothed energy divided by alpha_j (the kernel's internal form, so that a
+ * get/set round trip is bit-exact).                                                          */
+int frt_bank_state_size(frt_handle h, int64_t *z_floats, int64_t *ema_floats);
+int frt_bank_get_state(frt_handle h, float *z_host, float *ema_host);
+int frt_bank_set_state(frt_handle h, const float *z_host, const float *ema_host);
+
 #ifdef __cplusplus
 }
 #endif
