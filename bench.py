@@ -163,6 +163,38 @@ def _cpu_stft_step_vectorised(idx):
     return db.shape[0] * db.shape[1], float(db[0, 0, 0])
 
 
+def usable_cpus():
+    """CPUs this process may actually use: min(affinity, cgroup cpu.max quota)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(np.ceil(int(quota) / int(period)))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
+def best_cpu_baseline(n_channels, frames):
+    """The CPU path with the worker count that gives it the highest throughput on this host
+    (one or two workers per usable CPU)."""
+    ncpu = usable_cpus()
+    best = None
+    for workers in sorted({ncpu, min(2 * ncpu, os.cpu_count() or ncpu)}):
+        base = CpuBaseline(n_channels=max(n_channels, workers), frames_per_channel=frames,
+                           nproc=workers)
+        base.step()
+        n, dt = base.step()
+        if best is None or n / dt > best[1]:
+            if best is not None:
+                best[0].close()
+            best = (base, n / dt)
+        else:
+            base.close()
+    best[0].cores = ncpu
+    return best[0]
+
+
 class CpuBaseline:
     """Times the oracle port of the reference path on the host cores (multiprocessing, one
     worker per logical CPU, channels partitioned evenly)."""
@@ -194,9 +226,7 @@ def run_reference_arm(args, rank, world):
     """--impl reference: the CPU path alone.  Under torchrun only rank 0 works."""
     if rank != 0:
         return
-    ncpu = os.cpu_count() or 1
-    frames = 2048
-    base = CpuBaseline(n_channels=max(256, ncpu), frames_per_channel=frames)
+    base = best_cpu_baseline(256, 1024)
     for _ in range(max(args.warmup, 1)):
         base.step()
     tot_n, tot_t = 0, 0.0
@@ -212,8 +242,8 @@ def run_reference_arm(args, rank, world):
         "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, world),
-        "cpu_baseline": {"value": value, "unit": "spectra/s", "cores": base.nproc, "kind": "port",
-                         "sample": base.sample},
+        "cpu_baseline": {"value": value, "unit": "spectra/s", "cores": base.cores,
+                         "workers": base.nproc, "kind": "port", "sample": base.sample},
         "e2e": {"value": value, "unit": "spectra/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "note": "reference is pure Python/NumPy and cannot travel to the GPU box; this is oracle/, "
@@ -223,6 +253,84 @@ def run_reference_arm(args, rank, world):
 
 
 # ----------------------------------------------------------------------------- ours
+def other_workloads(args, dev, rank, world, barrier):
+    """Config #3 (1/3-octave bank + RMS), config #5's per-GPU unit (STFT column + band vector per
+    1024-sample hop) and, at N>1, the final NCCL all-gather of spectrogram columns.  Each is
+    timed over a few launches with CUDA events (max over ranks); these are explanatory extras."""
+    import torch
+    import torch.distributed as dist
+    from friture_b200 import audioproc
+    from friture_b200.octavefilters import Octave_Filters
+    from friture_b200.sharded import allgather_channels
+
+    def timed(fn, reps):
+        fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    res = {}
+    C = 1024
+    g = torch.Generator(device="cpu").manual_seed(99 + rank)
+    nblk = 64
+    x = (torch.randn((C, 1024 * nblk), generator=g, dtype=torch.float32) * 0.1).to(dev)
+    for name, bpo, noct, block in (("bank_27band_block512", 3, 9, 512),
+                                   ("bank_30band_block512", 3, 10, 512),
+                                   ("bank_27band_block1024", 3, 9, 1024)):
+        bank = Octave_Filters(bpo, device=dev.index, n_octaves=noct)
+        nb = x.shape[1] // block
+        ms = timed(lambda: bank.energies_batch(x, block=block, db=True), 3)
+        blocks = C * nb * world
+        # algorithmic bytes per block: input + band vector + state read/write (SURVEY 8d #3)
+        nsec = 2 * bpo + 6
+        byts = block * 4 + noct * bpo * 4 + 2 * (noct * nsec * 2 + noct * bpo) * 4 / nb
+        # FMA-class instructions per input sample: 5 per biquad step, 2 for x^2 + smoothing
+        fma = sum((nsec * 5 + bpo * 2) / 2 ** j for j in range(noct))
+        res[name] = {"channels_per_gpu": C, "blocks_per_channel": nb, "ms": ms,
+                     "blocks_per_s": blocks / (ms * 1e-3),
+                     "hbm_gbs_algorithmic": blocks / world * byts / (ms * 1e-3) / 1e9,
+                     "fp32_useful_tflops": 2 * blocks / world * block * fma / (ms * 1e-3) / 1e12,
+                     "note": "compute-bound recursion (FP32 issue / dependency latency), not HBM"}
+        del bank
+    # combined unit of config #5: per channel-hop one log-power column + one 27-band vector
+    proc = audioproc(handle=None)
+    proc.set_fftsize(N_FFT)
+    bank = Octave_Filters(3, device=dev.index)
+    xs = x[:, :N_FFT + (nblk - 2) * HOP]
+    outc = torch.empty((C, nblk - 1, NBINS), dtype=torch.float32, device=dev)
+
+    def combined():
+        proc.stft(xs, hop=HOP, log=True, out=outc)
+        bank.energies_batch(x[:, :1024 * (nblk - 1)], block=1024, db=True)
+    ms = timed(combined, 3)
+    res["combined_stft_plus_27band"] = {"channels_per_gpu": C, "hops_per_channel": nblk - 1, "ms": ms,
+                                        "units_per_s": C * (nblk - 1) * world / (ms * 1e-3)}
+    if world > 1:
+        # final all-gather of the spectrogram columns over NVLink (north_star); link-bound:
+        # every GPU must receive (world-1)/world of ALL columns
+        full = torch.empty((C * world, nblk - 1, NBINS), dtype=torch.float32, device=dev)
+
+        def stft_and_gather():
+            proc.stft(xs, hop=HOP, log=True, out=outc)
+            allgather_channels(outc, C * world, out=full)
+        ms_g = timed(stft_and_gather, 3)
+        ms_s = timed(lambda: proc.stft(xs, hop=HOP, log=True, out=outc), 3)
+        recv = outc.numel() * 4 * (world - 1)
+        res["stft_with_allgather"] = {"channels_per_gpu": C, "frames": nblk - 1, "ms_stft": ms_s,
+                                      "ms_stft_plus_allgather": ms_g,
+                                      "spectra_per_s": C * (nblk - 1) * world / (ms_g * 1e-3),
+                                      "allgather_recv_gbs_per_gpu": recv / max(ms_g - ms_s, 1e-6) / 1e6}
+    return res
+
+
 def workload_config(args, world):
     return {"workload": "configs[1]: %d ch/GPU x %d frames, 48 kHz, 2048-pt STFT hop 1024 (50%% overlap) "
                         "+ log-power spectrogram" % (args.channels, args.frames),
@@ -245,6 +353,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-others", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -368,19 +477,22 @@ def main():
         e2e["matches_device_path"] = same
         del xh, oh
 
+    # ---- other rows of the hot path, short runs (extra information, not the headline value)
+    others = {}
+    if not args.no_others:
+        others = other_workloads(args, dev, rank, world, barrier)
+
     # ---- CPU baseline on this host (rank 0, N=1 only)
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        ncpu = os.cpu_count() or 1
-        base = CpuBaseline(n_channels=max(256, ncpu), frames_per_channel=2048)
-        base.step()
+        base = best_cpu_baseline(256, 1024)
         n, dt = base.step()
         n2, dt2 = base.step()
         nv, dtv = base.step(_cpu_stft_step_vectorised)
         nv, dtv = base.step(_cpu_stft_step_vectorised)
         base.close()
-        cpu_baseline = {"value": (n + n2) / (dt + dt2), "unit": "spectra/s", "cores": base.nproc,
-                        "kind": "port", "sample": base.sample,
+        cpu_baseline = {"value": (n + n2) / (dt + dt2), "unit": "spectra/s", "cores": base.cores,
+                        "workers": base.nproc, "kind": "port", "sample": base.sample,
                         "vectorised_numpy_value": nv / dtv}
 
     if rank == 0:
@@ -390,7 +502,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(args, world),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": int(launches), "parity": perr,
+            "gpu_launches": int(launches), "parity": perr, "other_workloads": others,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -143,7 +143,8 @@ class audioproc():
             return out
         self._ensure_plan()
         sp = _lib.current_stream_ptr(x.device) if stream is None else c_void_p(int(stream))
-        self.handle.call("frt_stft_process", _lib._ptr(x), int(x.stride(0)), int(C), int(nf),
+        self.handle.call("frt_stft_process", _lib._ptr(x), int(x.stride(0)) if C > 1 else int(T),
+                         int(C), int(nf),
                          int(hop), _lib._ptr(out), int(nf * nb), int(nb),
                          STFT_LOGPOWER if log else STFT_POWER, sp)
         return out
@@ -169,6 +170,8 @@ class audioproc():
             return out
         self._ensure_plan()
         stride = int(x.stride(0)) if is_torch else int(x.strides[0] // 4)
+        if C == 1:
+            stride = T      # a length-1 axis may carry any stride
         self.handle.call("frt_stft_process_host", _lib._ptr(x), stride, int(C), int(T), int(hop),
                          _lib._ptr(out), STFT_LOGPOWER if log else STFT_POWER)
         return out

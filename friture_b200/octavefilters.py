@@ -223,7 +223,8 @@ class Octave_Filters():
             ystride = int(offsets[-1] + lengths[-1])
             ybuf = torch.empty((C, ystride), dtype=torch.float32, device=x.device)
         sp = _lib.current_stream_ptr(x.device) if stream is None else c_void_p(int(stream))
-        self.handle.call("frt_bank_process", _lib._ptr(x), int(x.stride(0)), int(block),
+        self.handle.call("frt_bank_process", _lib._ptr(x), int(x.stride(0)) if C > 1 else int(T),
+                         int(block),
                          int(n_blocks), _lib._ptr(e), _lib._ptr(ybuf), ystride,
                          1 if db else 0, sp)
         y = None
