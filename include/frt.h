@@ -111,6 +111,24 @@ int frt_bank_state_size(frt_handle h, int64_t *z_floats, int64_t *ema_floats);
 int frt_bank_get_state(frt_handle h, float *z_host, float *ema_host);
 int frt_bank_set_state(frt_handle h, const float *z_host, const float *ema_host);
 
+/* ---------------------------------------------------------------- GCC-PHAT (delay estimator)
+ * Stands behind `generalized_cross_correlation(d0, d1)` (friture/signal/correlation.py:24-43)
+ * and the smoothing + peak pick around it (friture/delay_estimator.py:129-142).               */
+
+/* Plan for frames of `length` samples (even, 2^a 3^b 5^c, <= 28160; the widget's default is
+ * 2 * delayrange_s * 12 kHz = 24000, delay_estimator.py:53-54,114-117).                       */
+int frt_gcc_plan(frt_handle h, int length);
+/* n_pairs independent channel pairs: d0/d1[p*stride + n].  Inputs are not modified (the
+ * reference subtracts the means in place, a side effect that is not reproduced).
+ *   xcorr_dev     NULL or [n_pairs][length]: this frame's Xcorr (correlation.py:41)
+ *   smoothed_dev  NULL or [n_pairs][length]: smoothed Xcorr, read when have_prev != 0
+ *                 (0.3*X + 0.7*old, delay_estimator.py:134-139) and always written
+ *   idx_dev/val_dev [n_pairs]: i = argmax |Xs| and Xs[i] (delay_estimator.py:141-146); pairs
+ *                 with a constant input (std == 0) give (0, 0) as in delay_estimator.py:129-131,164-167 */
+int frt_gcc_phat(frt_handle h, const float *d0_dev, const float *d1_dev, int64_t stride,
+                 int n_pairs, float *xcorr_dev, float *smoothed_dev, int have_prev, int *idx_dev,
+                 float *val_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
