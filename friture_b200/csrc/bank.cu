@@ -20,6 +20,7 @@
 // serially over the <=32 samples, which are broadcast with shuffles.
 // Filter and smoothing state lives in shared memory while the kernel runs (global in between).
 #include <cmath>
+#include <cstdlib>
 
 #include "frt_internal.cuh"
 
@@ -151,13 +152,13 @@ __device__ __forceinline__ void section_scan(const float (&in)[L], float (&out)[
 
 template <int N> __device__ void serial_stage(float xin, const WarpCtx &w, int j);
 
-// One scan-mode stage: L samples per lane, 32 lanes active.
+// Band chains of one scan-mode stage (bands bpo-1 .. 0, friture/filter.py:105) with the smoothing
+// of y^2: L samples per lane, 32 lanes active.
 template <int L>
-__device__ void scan_stage(const float (&xc)[L], const WarpCtx &w, int j) {
+__device__ __forceinline__ void bands_of_stage(const float (&xc)[L], const WarpCtx &w, int j) {
     const BankParams &P = *w.P;
     const int bpo = P.bpo;
     float wk[L];
-    // bands bpo-1 .. 0 (friture/filter.py:105)
     for (int i = bpo - 1; i >= 0; i--) {
         section_scan<L>(xc, wk, w, j, 2 * i);
         section_scan<L>(wk, wk, w, j, 2 * i + 1);
@@ -187,11 +188,27 @@ __device__ void scan_stage(const float (&xc)[L], const WarpCtx &w, int j) {
             if (w.energies) w.energies[kband] = energy_out(P.alpha[j] * e, w.db);
         }
     }
-    if (j + 1 >= P.n_oct) return;   // the last decimator's output is discarded (filter.py:113)
-    // decimator: 6 sections, then keep even samples (friture/signal/decimate.py:39-41)
+}
+
+// Decimation low-pass of one scan-mode stage: 6 sections, full-rate output in wk
+// (the caller keeps the even samples, friture/signal/decimate.py:39-41).
+template <int L>
+__device__ __forceinline__ void dec_of_stage(const float (&xc)[L], float (&wk)[L], const WarpCtx &w,
+                                             int j) {
+    const int bpo = w.P->bpo;
     section_scan<L>(xc, wk, w, j, 2 * bpo);
 #pragma unroll 1
     for (int s = 1; s < 6; s++) section_scan<L>(wk, wk, w, j, 2 * bpo + s);
+}
+
+// One scan-mode stage, single-warp variant: bands, then the decimator, then the next stage.
+template <int L>
+__device__ void scan_stage(const float (&xc)[L], const WarpCtx &w, int j) {
+    const BankParams &P = *w.P;
+    bands_of_stage<L>(xc, w, j);
+    if (j + 1 >= P.n_oct) return;   // the last decimator's output is discarded (filter.py:113)
+    float wk[L];
+    dec_of_stage<L>(xc, wk, w, j);
     if constexpr (L >= 4) {
         float xn[L / 2];
 #pragma unroll
@@ -200,6 +217,47 @@ __device__ void scan_stage(const float (&xc)[L], const WarpCtx &w, int j) {
     } else {
         // L == 2: one sample per lane is left -> switch to lane = chain
         serial_stage<32>(wk[0], w, j + 1);
+    }
+}
+
+// ---- three-warp variant (one CTA of 96 threads per channel) --------------------------------
+// warp 0 "D": decimator chain of the scan-mode stages (the critical path to the next stage),
+// warp 1 "B": band chains of the scan-mode stages, one barrier behind D per stage,
+// warp 2 "S": the low-rate serial stages of the PREVIOUS tile.
+// D hands the decimated chunks to B through shared memory; named barrier 1 (64 threads) paces
+// D and B stage by stage, __syncthreads() closes a tile.
+__device__ __forceinline__ void bar_db() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
+
+template <int L>
+__device__ void stage_D(const float (&xc)[L], const WarpCtx &w, int j, float *s_x, float *s_x32) {
+    float wk[L];
+    dec_of_stage<L>(xc, wk, w, j);
+    if constexpr (L >= 4) {
+        float xn[L / 2];
+        float *dst = s_x + w.lane * (L / 2);     // stage j+1 chunk of this lane
+#pragma unroll
+        for (int k = 0; k < L / 2; k++) {
+            xn[k] = wk[2 * k];
+            dst[k] = xn[k];
+        }
+        bar_db();
+        stage_D<L / 2>(xn, w, j + 1, s_x + 32 * (L / 2), s_x32);
+    } else {
+        s_x32[w.lane] = wk[0];                   // 32 samples for the serial stages (warp S)
+        bar_db();
+    }
+}
+
+template <int L>
+__device__ void stage_B(const float (&xc)[L], const WarpCtx &w, int j, const float *s_x) {
+    bands_of_stage<L>(xc, w, j);
+    bar_db();
+    if constexpr (L >= 4) {
+        float xn[L / 2];
+        const float *src = s_x + w.lane * (L / 2);
+#pragma unroll
+        for (int k = 0; k < L / 2; k++) xn[k] = src[k];
+        stage_B<L / 2>(xn, w, j + 1, s_x + 32 * (L / 2));
     }
 }
 
@@ -232,8 +290,8 @@ __device__ void serial_stage(float xin, const WarpCtx &w, int j) {
     if (w.y && is_band)
         yp = w.y + y_offset(kband, bpo, P.n_oct, w.t_total) + (w.t_off >> j);
     float xnext = 0.f;
-#pragma unroll
-    for (int m = 0; m < N; m++) {
+#pragma unroll 1
+    for (int m = 0; m < N; m++) {   // rolled on purpose: instruction-cache footprint matters here
         float v = __shfl_sync(0xffffffffu, xin, m);
 #pragma unroll
         for (int s = 0; s < 6; s++) {
@@ -334,6 +392,78 @@ bank_kernel(const __grid_constant__ BankParams P, const BankArgs a) {
     float *ge = a.ema + (size_t)c * ne;
     for (int i = lane; i < nz; i += 32) gz[i] = s_z[i];
     for (int i = lane; i < ne; i += 32) ge[i] = s_e[i];
+}
+
+template <int L0>
+__global__ void __launch_bounds__(96)
+bank_kernel3(const __grid_constant__ BankParams P, const BankArgs a) {
+    extern __shared__ float smem[];
+    const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+    const int nz = P.n_oct * P.nsec * 2, ne = P.n_oct * P.bpo;
+    constexpr int TILE = 32 * L0;
+    float *s_coef = smem;                        // [nsec][8]
+    float *s_z = s_coef + P.nsec * 8;            // this channel's filter state
+    float *s_e = s_z + nz;                       // this channel's smoothing state
+    float *s_x = s_e + ne;                       // chunks of stages 1.. (TILE/2 + TILE/4 + ...)
+    float *s_x32 = s_x + TILE;                   // [2][32] double-buffered input of the serial stages
+    const int c = blockIdx.x;
+    for (int i = threadIdx.x; i < P.nsec * 8; i += blockDim.x) s_coef[i] = P.coef[i >> 3][i & 7];
+    {
+        const float *gz = a.zstate + (size_t)c * nz;
+        const float *ge = a.ema + (size_t)c * ne;
+        for (int i = threadIdx.x; i < nz; i += blockDim.x) s_z[i] = gz[i];
+        for (int i = threadIdx.x; i < ne; i += blockDim.x) s_e[i] = ge[i];
+    }
+    __syncthreads();
+    const int nbands = P.n_oct * P.bpo;
+    WarpCtx w;
+    w.P = &P;
+    w.s_z = s_z;
+    w.s_e = s_e;
+    w.s_coef = s_coef;
+    w.lane = lane;
+    w.db = a.db;
+    w.t_total = a.t_total;
+    w.y = a.y ? a.y + (size_t)c * a.y_stride : nullptr;
+    const float *xch = a.x + (size_t)c * a.x_stride;
+    const int n_blocks = a.n_tiles / a.tiles_per_block;
+    constexpr int NSCAN = Log2<L0>::v;           // scan-mode stages 0 .. NSCAN-1 (L = L0 .. 2)
+    for (int t = 0; t <= a.n_tiles; t++) {
+        if (role < 2 && t < a.n_tiles) {
+            const float *xp = xch + (size_t)t * TILE + lane * L0;
+            float xc[L0];
+            if (a.vec_ok) {
+#pragma unroll
+                for (int k = 0; k < L0; k += 4) {
+                    const float4 v = __ldg(reinterpret_cast<const float4 *>(xp + k));
+                    xc[k] = v.x; xc[k + 1] = v.y; xc[k + 2] = v.z; xc[k + 3] = v.w;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < L0; k++) xc[k] = __ldg(xp + k);
+            }
+            const bool block_end = ((t + 1) % a.tiles_per_block) == 0;
+            w.energies = (a.energies && block_end)
+                             ? a.energies + ((size_t)c * n_blocks + t / a.tiles_per_block) * nbands
+                             : nullptr;
+            w.t_off = (long long)t * TILE;
+            if (role == 0) stage_D<L0>(xc, w, 0, s_x, s_x32 + (t & 1) * 32);
+            else stage_B<L0>(xc, w, 0, s_x);
+        } else if (role == 2 && t >= 1) {
+            const int tp = t - 1;
+            const bool block_end = ((tp + 1) % a.tiles_per_block) == 0;
+            w.energies = (a.energies && block_end)
+                             ? a.energies + ((size_t)c * n_blocks + tp / a.tiles_per_block) * nbands
+                             : nullptr;
+            w.t_off = (long long)tp * TILE;
+            if (NSCAN < P.n_oct) serial_stage<32>(s_x32[(tp & 1) * 32 + lane], w, NSCAN);
+        }
+        __syncthreads();
+    }
+    float *gz = a.zstate + (size_t)c * nz;
+    float *ge = a.ema + (size_t)c * ne;
+    for (int i = threadIdx.x; i < nz; i += blockDim.x) gz[i] = s_z[i];
+    for (int i = threadIdx.x; i < ne; i += blockDim.x) ge[i] = s_e[i];
 }
 
 }   // namespace
@@ -480,7 +610,23 @@ extern "C" int frt_bank_set_state(frt_handle h, const float *z_host, const float
 }
 
 template <int L0>
+static cudaError_t launch_bank3(const BankPlan *pl, const BankArgs &a, cudaStream_t st) {
+    const BankParams &P = pl->params;
+    const size_t smem = sizeof(float) * ((size_t)P.nsec * 8 + pl->nz + pl->ne + 32 * L0 + 64);
+    cudaError_t e = cudaFuncSetAttribute(bank_kernel3<L0>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    bank_kernel3<L0><<<(unsigned)a.n_channels, 96, smem, st>>>(P, a);
+    return cudaGetLastError();
+}
+
+template <int L0>
 static cudaError_t launch_bank(const BankPlan *pl, const BankArgs &a, cudaStream_t st) {
+    // few channels: three warps per channel (latency-bound regime); many channels: one warp
+    // per channel already saturates the schedulers with less synchronisation
+    static const char *force = getenv("FRT_BANK_WARPS");
+    const bool three = force ? (force[0] == '3') : (a.n_channels < 6144);
+    if (three) return launch_bank3<L0>(pl, a, st);
     const BankParams &P = pl->params;
     const int warps = 2;
     const size_t smem = sizeof(float) * ((size_t)P.nsec * 8 + (size_t)warps * (pl->nz + pl->ne));

@@ -90,12 +90,19 @@ __device__ __forceinline__ void dif_pass(float2 *z, int L, int n, const float2 *
         for (int q = 0; q < R; q++) v[q] = p[q * n_next];
         dft<R>(v);
         p[0] = v[0];
+        // W_n^(j q), q = 1..R-1: one table read, the rest by successive products
+        const float2 w1 = __ldg(tw + (size_t)j * tw_step);
+        float2 wq = w1;
+        p[n_next] = cmul(v[1], w1);
 #pragma unroll
-        for (int q = 1; q < R; q++) p[q * n_next] = cmul(v[q], __ldg(tw + (size_t)j * q * tw_step));
+        for (int q = 2; q < R; q++) {
+            wq = cmul(wq, w1);
+            p[q * n_next] = cmul(v[q], wq);
+        }
     }
 }
 
-__device__ void fft_inplace(float2 *z, int L, const GccRadices &rd, const float2 *__restrict__ tw) {
+__device__ __noinline__ void fft_inplace(float2 *z, int L, const GccRadices &rd, const float2 *__restrict__ tw) {
     int n = L;
     for (int i = 0; i < rd.n_passes; i++) {
         const int r = rd.radix[i];
@@ -109,7 +116,7 @@ __device__ void fft_inplace(float2 *z, int L, const GccRadices &rd, const float2
 }
 
 // storage position of frequency (or time) index k after the in-place DIF passes
-__device__ __forceinline__ int digit_reverse(int k, int L, const GccRadices &rd) {
+static int digit_reverse(int k, int L, const GccRadices &rd) {
     int pos = 0, n = L;
     for (int i = 0; i < rd.n_passes; i++) {
         const int r = rd.radix[i];
@@ -157,6 +164,7 @@ struct GccArgs {
     int n_pairs, L;
     const float *window;       // [L] np.hanning(L)
     const float2 *tw;          // [L] W_L^i
+    const int *perm;           // [L] storage position of index k after the in-place DIF passes
     float *xcorr;              // [n_pairs][L] or NULL: raw Xcorr of this frame
     float *smoothed;           // [n_pairs][L] or NULL: in (if have_prev) / out smoothed Xcorr
     int have_prev;
@@ -214,8 +222,8 @@ __global__ void __launch_bounds__(GCC_THREADS, 1) gcc_phat_kernel(const GccArgs 
             const int k = tid + i * nt;
             g[i] = make_float2(0.f, 0.f);
             if (k <= half) {
-                const float2 zk = z[digit_reverse(k, L, a.rd)];
-                const float2 zm = z[digit_reverse(k == 0 ? 0 : L - k, L, a.rd)];
+                const float2 zk = z[__ldg(a.perm + k)];
+                const float2 zm = z[__ldg(a.perm + (k == 0 ? 0 : L - k))];
                 // D0 = (Zk + conj Zm)/2 ; D1 = (Zk - conj Zm)/(2j)
                 const float2 D0 = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
                 const float2 D1 = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));
@@ -248,7 +256,7 @@ __global__ void __launch_bounds__(GCC_THREADS, 1) gcc_phat_kernel(const GccArgs 
         float *sm = a.smoothed ? a.smoothed + (size_t)pair * L : nullptr;
         float *xc = a.xcorr ? a.xcorr + (size_t)pair * L : nullptr;
         for (int n = tid; n < L; n += nt) {
-            float v = z[digit_reverse(n, L, a.rd)].x * inv;
+            float v = z[__ldg(a.perm + n)].x * inv;
             if (xc) xc[n] = v;
             if (sm) {
                 if (a.have_prev) v = 0.3f * v + 0.7f * sm[n];
@@ -291,7 +299,7 @@ __global__ void __launch_bounds__(GCC_THREADS, 1) gcc_phat_kernel(const GccArgs 
         __syncthreads();
         if (tid == 0) {
             const int bi = s_idx[32];
-            float v = z[digit_reverse(bi, L, a.rd)].x * inv;
+            float v = z[__ldg(a.perm + bi)].x * inv;
             if (sm) v = sm[bi];
             a.idx[pair] = bi;
             a.val[pair] = v;
@@ -306,6 +314,7 @@ struct GccPlan {
     int L = 0;
     float *window = nullptr;
     float2 *tw = nullptr;
+    int *perm = nullptr;
     GccRadices rd;
 };
 
@@ -313,6 +322,7 @@ void frt_gcc_release(frt_ctx *h) {
     if (!h->gcc) return;
     if (h->gcc->window) cudaFree(h->gcc->window);
     if (h->gcc->tw) cudaFree(h->gcc->tw);
+    if (h->gcc->perm) cudaFree(h->gcc->perm);
     delete h->gcc;
     h->gcc = nullptr;
 }
@@ -349,7 +359,12 @@ extern "C" int frt_gcc_plan(frt_handle h, int length) {
         const double ang = -2.0 * PI * (double)i / (double)length;
         tw[i] = make_float2((float)cos(ang), (float)sin(ang));
     }
+    std::vector<int> perm(length);
+    for (int i = 0; i < length; i++) perm[i] = digit_reverse(i, length, rd);
     cudaError_t e = cudaMalloc(&pl->window, sizeof(float) * length);
+    if (e == cudaSuccess) e = cudaMalloc(&pl->perm, sizeof(int) * length);
+    if (e == cudaSuccess)
+        e = cudaMemcpy(pl->perm, perm.data(), sizeof(int) * length, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc(&pl->tw, sizeof(float2) * length);
     if (e == cudaSuccess)
         e = cudaMemcpy(pl->window, win.data(), sizeof(float) * length, cudaMemcpyHostToDevice);
@@ -361,6 +376,7 @@ extern "C" int frt_gcc_plan(frt_handle h, int length) {
     if (e != cudaSuccess) {
         if (pl->window) cudaFree(pl->window);
         if (pl->tw) cudaFree(pl->tw);
+        if (pl->perm) cudaFree(pl->perm);
         delete pl;
         return frt_fail(h, FRT_ECUDA, "frt_gcc_plan: %s", cudaGetErrorString(e));
     }
@@ -388,6 +404,7 @@ extern "C" int frt_gcc_phat(frt_handle h, const float *d0_dev, const float *d1_d
     a.L = pl->L;
     a.window = pl->window;
     a.tw = pl->tw;
+    a.perm = pl->perm;
     a.xcorr = xcorr_dev;
     a.smoothed = smoothed_dev;
     a.have_prev = have_prev;
