@@ -222,6 +222,70 @@ class CpuBaseline:
         self.pool.join()
 
 
+def _cpu_bank_c(arg):
+    """IIR bank + smoothing through the plain-C restatement (oracle/iir_df2t.c)."""
+    seed, nch, nblk = arg
+    from oracle import friture_oracle as fo
+    from oracle import iir_c
+    from friture_b200 import filter_data
+    bdec, adec, _ = filter_data.decimator()
+    boct, aoct, _ = filter_data.bands(3)
+    orc = fo.OctaveSpectrumOracle(bdec, adec, list(boct), list(aoct))
+    bank = iir_c.BankC(bdec, adec, list(boct), list(aoct), orc.alphas, n_channels=nch)
+    x = (np.random.default_rng(seed).standard_normal((nch, 512 * nblk)) * 0.1).astype(np.float32)
+    t0 = time.perf_counter()
+    bank.process(x, 512)
+    return nch * nblk, time.perf_counter() - t0
+
+
+def _cpu_gcc(arg):
+    seed, npairs = arg
+    from oracle import friture_oracle as fo
+    rng = np.random.default_rng(seed)
+    d0 = rng.standard_normal((npairs, 24000))
+    d1 = np.roll(d0, 137, axis=1) + 0.1 * rng.standard_normal((npairs, 24000))
+    t0 = time.perf_counter()
+    for p in range(npairs):
+        xc = fo.generalized_cross_correlation(d0[p], d1[p])
+        fo.delay_peak(xc)
+    return npairs, time.perf_counter() - t0
+
+
+def cpu_other_rows(workers):
+    """CPU path of the other rows on the usable host cores: the IIR bank (C restatement of the
+    reference's recursion, all workers; and the literal pure-Python loop on one block for the
+    true reference cost) and GCC-PHAT (NumPy, as the reference)."""
+    import multiprocessing as mp
+    from oracle import friture_oracle as fo
+    from friture_b200 import filter_data
+    out = {}
+    ctx = mp.get_context("fork")
+    with ctx.Pool(workers) as pool:
+        r = pool.map(_cpu_bank_c, [(100 + i, 4, 64) for i in range(workers)])
+        wall = max(t for _, t in r)
+        out["bank_27band_block512_c_port"] = {"blocks_per_s": sum(n for n, _ in r) / wall,
+                                              "workers": workers, "kind": "port (C, -O2, no FMA)"}
+        r = pool.map(_cpu_gcc, [(200 + i, 8) for i in range(workers)])
+        wall = max(t for _, t in r)
+        out["gcc_phat_L24000_numpy"] = {"pairs_per_s": sum(n for n, _ in r) / wall, "workers": workers,
+                                        "kind": "port (numpy.fft, as the reference)"}
+    bdec, adec, _ = filter_data.decimator()
+    boct, aoct, _ = filter_data.bands(3)
+    zis = fo.bank_filtic(bdec, adec, list(boct), list(aoct))
+    x = np.random.default_rng(0).standard_normal(512) * 0.1
+    t0 = time.perf_counter()
+    y = x
+    zi = 0
+    for j in range(9):          # literal pure-Python recursion of friture/signal/lfilter.py:131-139
+        for i in (2, 1, 0):
+            fo.lfilter_df2t_loop(boct[i], aoct[i], y, zis[zi]); zi += 1
+        yd, _ = fo.lfilter_df2t_loop(bdec, adec, y, zis[zi]); zi += 1
+        y = yd[::2]
+    out["bank_27band_block512_python_loop_1core"] = {"blocks_per_s": 1.0 / (time.perf_counter() - t0),
+                                                     "kind": "literal reference recursion, 1 core"}
+    return out
+
+
 def run_reference_arm(args, rank, world):
     """--impl reference: the CPU path alone.  Under torchrun only rank 0 works."""
     if rank != 0:
@@ -313,6 +377,18 @@ def other_workloads(args, dev, rank, world, barrier):
     ms = timed(combined, 3)
     res["combined_stft_plus_27band"] = {"channels_per_gpu": C, "hops_per_channel": nblk - 1, "ms": ms,
                                         "units_per_s": C * (nblk - 1) * world / (ms * 1e-3)}
+    # config #4: GCC-PHAT delay estimation, 4096 pairs x L = 24000 (12 kHz-rate signals)
+    from friture_b200.correlation import GccPhat
+    Pn, Lg = 4096, 24000
+    d0 = torch.randn((Pn, Lg), generator=g, dtype=torch.float32).to(dev)
+    d1 = torch.roll(d0, 137, 1) + 0.1 * torch.randn((Pn, Lg), generator=g, dtype=torch.float32).to(dev)
+    est = GccPhat(Lg)
+    ms = timed(lambda: est.estimate(d0, d1, smooth=False), 3)
+    idx, _, _ = est.estimate(d0, d1, smooth=False)
+    res["gcc_phat_4096pairs_L24000"] = {"ms": ms, "pairs_per_s": Pn * world / (ms * 1e-3),
+                                        "hbm_gbs_algorithmic": Pn * 2 * Lg * 4 / (ms * 1e-3) / 1e9,
+                                        "delays_recovered": bool((idx == 137).all().item())}
+    del d0, d1, est
     if world > 1:
         # final all-gather of the spectrogram columns over NVLink (north_star); link-bound:
         # every GPU must receive (world-1)/world of ALL columns
@@ -344,7 +420,7 @@ def workload_config(args, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="stft", choices=["stft"])
@@ -494,6 +570,8 @@ def main():
         cpu_baseline = {"value": (n + n2) / (dt + dt2), "unit": "spectra/s", "cores": base.cores,
                         "workers": base.nproc, "kind": "port", "sample": base.sample,
                         "vectorised_numpy_value": nv / dtv}
+        if not args.no_others:
+            cpu_baseline["other_rows"] = cpu_other_rows(base.cores)
 
     if rank == 0:
         line = {

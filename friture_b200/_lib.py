@@ -32,7 +32,8 @@ class FrtValueError(FrtError, ValueError):
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, _LIB_NAME)
+    # FRT_B200_LIB: tuning knob to A/B another build of the same library
+    return os.environ.get("FRT_B200_LIB") or os.path.join(_HERE, _LIB_NAME)
 
 
 # every exported symbol with (restype, argtypes); tests check that the built library exports

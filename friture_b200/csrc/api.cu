@@ -105,6 +105,7 @@ extern "C" int frt_destroy(frt_handle h) {
     if (h->stft.win_dev) cudaFree(h->stft.win_dev);
     if (h->stft.tw_dev) cudaFree(h->stft.tw_dev);
     if (h->stft.post_dev) cudaFree(h->stft.post_dev);
+    if (h->stft.wlane_dev) cudaFree(h->stft.wlane_dev);
     frt_bank_release(h);
     frt_gcc_release(h);
     pipe_release(h);

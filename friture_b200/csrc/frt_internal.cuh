@@ -15,6 +15,7 @@ struct StftPlan {
     float *win_dev = nullptr;      // [n_fft] symmetric Hann (audioproc.py:76-81)
     float2 *tw_dev = nullptr;      // fast path: [32][32] W_M^(k1*t); generic: [M] W_M^k
     float2 *post_dev = nullptr;    // [M/2+1] U[k] = -j*W_N^k (real-FFT split twiddles)
+    float2 *wlane_dev = nullptr;   // fast path: per-lane Hann phase factors
     std::vector<float> win_host;
 };
 
