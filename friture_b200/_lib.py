@@ -64,6 +64,9 @@ SIGNATURES = {
     "frt_gcc_plan": (c_int, [c_void_p, c_int]),
     "frt_gcc_phat": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int,
                              c_void_p, c_void_p, c_void_p]),
+    "frt_spectrum_reduce": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int,
+                                    c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_void_p]),
 }
 
 _lib = None

@@ -129,6 +129,20 @@ int frt_gcc_phat(frt_handle h, const float *d0_dev, const float *d1_dev, int64_t
                  int n_pairs, float *xcorr_dev, float *smoothed_dev, int have_prev, int *idx_dev,
                  float *val_dev, void *stream);
 
+/* ---------------------------------------------------------------- spectrum widget reductions
+ * The per-tick numeric work of Spectrum_Widget.handle_new_data behind the STFT
+ * (friture/spectrum.py:158-181): smoothing across the tick's frames
+ * (exp_smoothed_value_2d, friture/signal/exp_smoothing.py:59-107, alpha from spectrum.py:196-218),
+ * 10*log10(sp+1e-30) + weighting (spectrum.py:95-101,171), arg-max (spectrum.py:175) and the
+ * 3-harmonic product spectrum arg-max (spectrum.py:103-123,179-181).
+ *   power_dev [C][n_frames][nbins] (strides in floats), disp_dev [C][nbins] smoothed power in/out
+ *   (the widget's dispbuffers1), weight_dev [nbins] dB offsets or NULL, db_dev [C][nbins],
+ *   fmax_idx_dev / pitch_idx_dev [C].                                                          */
+int frt_spectrum_reduce(frt_handle h, const float *power_dev, int64_t stride_c, int64_t stride_f,
+                        int n_channels, int n_frames, int nbins, float alpha, float *disp_dev,
+                        const float *weight_dev, float *db_dev, int *fmax_idx_dev,
+                        int *pitch_idx_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -311,3 +311,28 @@ def harmonic_product_spectrum(sp):
     """sp[:h]*sp[::2][:h]*sp[::3][:h], h=len//3: friture/spectrum.py:103-123."""
     h = sp.shape[0] // 3
     return sp[:h] * sp[::2][:h] * sp[::3][:h]
+
+
+class SpectrumWidgetOracle:
+    """Numeric part of Spectrum_Widget.handle_new_data for one channel
+    (friture/spectrum.py:125-184 with setresponsetime :196-218): per tick, `analyzelive` on every
+    realizable frame, exp_smoothed_value_2d across them, dB + weighting, arg-max, HPS arg-max."""
+
+    def __init__(self, fft_size, overlap=0.75, response_time=0.025, weight=None):
+        self.fft_size = fft_size
+        self.hop = int(fft_size * (1. - overlap))
+        n = response_time * SAMPLING_RATE / (fft_size * (1. - overlap))
+        self.alpha = 1. - (1. - 0.65) ** (1. / (n + 1))
+        self.kernel = smoothing_kernel(self.alpha, 2 * 4096)
+        self.freq = np.linspace(0, SAMPLING_RATE // 2, fft_size // 2 + 1)
+        self.w = np.zeros(fft_size // 2 + 1) if weight is None else weight
+        self.disp = np.zeros(fft_size // 2 + 1)
+
+    def tick(self, x):
+        spn = stft_power(x, self.fft_size, self.hop).T           # [bins, realizable]
+        sp = exp_smoothed_value_2d(self.kernel, self.alpha, spn, self.disp)
+        self.disp = sp
+        db = log_spectrogram(sp) + self.w
+        i = int(np.argmax(db))
+        pitch = int(np.argmax(harmonic_product_spectrum(sp)))
+        return db, self.freq[i], max(self.freq[pitch], 1e-20), i, pitch
