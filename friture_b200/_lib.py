@@ -67,6 +67,8 @@ SIGNATURES = {
     "frt_spectrum_reduce": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int,
                                     c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_void_p]),
+    "frt_decimate_plan": (c_int, [c_void_p, c_int, c_int, c_void_p]),
+    "frt_decimate_process": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
 }
 
 _lib = None

@@ -108,6 +108,7 @@ extern "C" int frt_destroy(frt_handle h) {
     if (h->stft.wlane_dev) cudaFree(h->stft.wlane_dev);
     frt_bank_release(h);
     frt_gcc_release(h);
+    frt_dec_release(h);
     pipe_release(h);
     delete h;
     return FRT_OK;

@@ -466,6 +466,71 @@ bank_kernel3(const __grid_constant__ BankParams P, const BankArgs a) {
     for (int i = threadIdx.x; i < ne; i += blockDim.x) ge[i] = s_e[i];
 }
 
+// ---- stand-alone N-fold decimation (decimate_multiple, friture/signal/decimate.py:45-71) ------
+// The same 6-section low-pass as the bank's decimator, run NDEC times with [::2] in between, one
+// warp per channel, tiles of 256 samples (L = 8, 4, ... per lane).  Used by the delay estimator
+// (48 kHz -> 12 kHz with Ndec = 2, friture/delay_estimator.py:53-59,97-98).
+struct DecArgs {
+    const float *x;
+    long long x_stride;
+    float *out;
+    long long out_stride;
+    int n_channels, n_tiles, n_stages;
+    float *zstate;   // [C][n_stages][6][2]
+};
+
+template <int L>
+__device__ void dec_chain(const float (&xc)[L], const WarpCtx &w, int j, int n_stages, float *dst) {
+    float wk[L];
+    dec_of_stage<L>(xc, wk, w, j);
+    if (j + 1 == n_stages) {
+#pragma unroll
+        for (int k = 0; k < L / 2; k++) dst[w.lane * (L / 2) + k] = wk[2 * k];
+        return;
+    }
+    if constexpr (L >= 4) {
+        float xn[L / 2];
+#pragma unroll
+        for (int k = 0; k < L / 2; k++) xn[k] = wk[2 * k];
+        dec_chain<L / 2>(xn, w, j + 1, n_stages, dst);
+    }
+}
+
+__global__ void __launch_bounds__(64)
+decimate_kernel(const __grid_constant__ BankParams P, const DecArgs a) {
+    extern __shared__ float smem[];
+    constexpr int L0 = 8, TILE = 256;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    const int nz = a.n_stages * P.nsec * 2;
+    float *s_z = smem + wid * nz;
+    const int c = blockIdx.x * warps + wid;
+    if (c >= a.n_channels) return;
+    float *gz = a.zstate + (size_t)c * nz;
+    for (int i = lane; i < nz; i += 32) s_z[i] = gz[i];
+    __syncwarp();
+    WarpCtx w;
+    w.P = &P;
+    w.s_z = s_z;
+    w.s_e = nullptr;
+    w.s_coef = nullptr;
+    w.energies = nullptr;
+    w.y = nullptr;
+    w.lane = lane;
+    w.db = 0;
+    w.t_total = 0;
+    w.t_off = 0;
+    const int out_tile = TILE >> a.n_stages;
+    for (int t = 0; t < a.n_tiles; t++) {
+        const float *xp = a.x + (size_t)c * a.x_stride + (size_t)t * TILE + lane * L0;
+        float xc[L0];
+#pragma unroll
+        for (int k = 0; k < L0; k++) xc[k] = __ldg(xp + k);
+        dec_chain<L0>(xc, w, 0, a.n_stages, a.out + (size_t)c * a.out_stride + (size_t)t * out_tile);
+        __syncwarp();
+    }
+    for (int i = lane; i < nz; i += 32) gz[i] = s_z[i];
+}
+
 }   // namespace
 
 struct BankPlan {
@@ -683,5 +748,98 @@ extern "C" int frt_bank_process(frt_handle h, const float *x_dev, int64_t x_stri
     h->launches++;
     if (e != cudaSuccess)
         return frt_fail(h, FRT_ECUDA, "bank kernel launch: %s", cudaGetErrorString(e));
+    return FRT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+struct DecPlan {
+    BankParams params;
+    int n_channels = 0, n_stages = 0;
+    float *zstate = nullptr;
+};
+
+static DecPlan *g_unused_decplan = nullptr;   // (plans live in the handle; see frt_ctx::dec)
+
+void frt_dec_release(frt_ctx *h) {
+    DecPlan *pl = reinterpret_cast<DecPlan *>(h->dec);
+    if (!pl) return;
+    if (pl->zstate) cudaFree(pl->zstate);
+    delete pl;
+    h->dec = nullptr;
+    (void)g_unused_decplan;
+}
+
+extern "C" int frt_decimate_plan(frt_handle h, int n_channels, int n_stages, const double *sos_dec) {
+    if (!h) return FRT_EINVAL;
+    DeviceGuard g(h->device);
+    FRT_CHECK_ARG(h, n_channels >= 1, "n_channels must be >= 1");
+    FRT_CHECK_ARG(h, n_stages >= 1 && n_stages <= 2, "n_stages must be 1 or 2");
+    FRT_CHECK_ARG(h, sos_dec != nullptr, "NULL coefficient table");
+    frt_dec_release(h);
+    DecPlan *pl = new (std::nothrow) DecPlan();
+    if (!pl) return frt_fail(h, FRT_ENOMEM, "out of host memory");
+    BankParams &P = pl->params;
+    memset(&P, 0, sizeof(P));
+    P.bpo = 0;          // section index 2*bpo + s = s: the six decimator sections
+    P.n_oct = n_stages;
+    P.nsec = 6;
+    for (int sec = 0; sec < 6; sec++) {
+        const double *s = sos_dec + (size_t)sec * 6;
+        P.coef[sec][0] = (float)s[0]; P.coef[sec][1] = (float)s[1]; P.coef[sec][2] = (float)s[2];
+        P.coef[sec][3] = (float)s[4]; P.coef[sec][4] = (float)s[5];
+        const double fb0 = P.coef[sec][0], fb1 = P.coef[sec][1], fb2 = P.coef[sec][2];
+        const double fa1 = P.coef[sec][3], fa2 = P.coef[sec][4];
+        P.coef[sec][5] = (float)(fb1 - fa1 * fb0);
+        P.coef[sec][6] = (float)(fb2 - fa2 * fb0);
+        double A[4] = {-fa1, 1.0, -fa2, 0.0};
+        for (int q = 0; q < NQ; q++) {
+            for (int i = 0; i < 4; i++) P.apow[sec][q][i] = (float)A[i];
+            double A2[4];
+            mat2_mul(A, A, A2);
+            memcpy(A, A2, sizeof(A));
+        }
+    }
+    pl->n_channels = n_channels;
+    pl->n_stages = n_stages;
+    const size_t nz = (size_t)n_stages * 6 * 2 * n_channels;
+    cudaError_t e = cudaMalloc(&pl->zstate, sizeof(float) * nz);
+    if (e == cudaSuccess) e = cudaMemset(pl->zstate, 0, sizeof(float) * nz);
+    if (e != cudaSuccess) {
+        if (pl->zstate) cudaFree(pl->zstate);
+        delete pl;
+        return frt_fail(h, FRT_ECUDA, "frt_decimate_plan: %s", cudaGetErrorString(e));
+    }
+    h->dec = pl;
+    return FRT_OK;
+}
+
+extern "C" int frt_decimate_process(frt_handle h, const float *x_dev, int64_t x_stride,
+                                    int64_t n_samples, float *out_dev, int64_t out_stride,
+                                    void *stream) {
+    if (!h) return FRT_EINVAL;
+    DecPlan *pl = reinterpret_cast<DecPlan *>(h->dec);
+    if (!pl) return frt_fail(h, FRT_ESTATE, "frt_decimate_process: call frt_decimate_plan first");
+    DeviceGuard g(h->device);
+    FRT_CHECK_ARG(h, n_samples >= 0, "negative length");
+    if (n_samples == 0) return FRT_OK;   // decimate_multiple returns empty input unchanged (:56-57)
+    FRT_CHECK_ARG(h, n_samples % 256 == 0, "n_samples must be a multiple of 256");
+    FRT_CHECK_ARG(h, x_dev && out_dev, "NULL buffer");
+    FRT_CHECK_ARG(h, x_stride >= n_samples && out_stride >= (n_samples >> pl->n_stages),
+                  "stride too small");
+    DecArgs a;
+    a.x = x_dev;
+    a.x_stride = x_stride;
+    a.out = out_dev;
+    a.out_stride = out_stride;
+    a.n_channels = pl->n_channels;
+    a.n_tiles = (int)(n_samples / 256);
+    a.n_stages = pl->n_stages;
+    a.zstate = pl->zstate;
+    const int warps = 2;
+    const size_t smem = sizeof(float) * warps * pl->n_stages * 12;
+    decimate_kernel<<<(pl->n_channels + warps - 1) / warps, warps * 32, smem,
+                      (cudaStream_t)stream>>>(pl->params, a);
+    h->launches++;
+    FRT_CUDA(h, cudaGetLastError());
     return FRT_OK;
 }

@@ -40,6 +40,7 @@ struct frt_ctx {
     HostPipe pipe;
     BankPlan *bank = nullptr;
     GccPlan *gcc = nullptr;
+    void *dec = nullptr;          // DecPlan (bank.cu)
 };
 
 int frt_fail(frt_ctx *h, int code, const char *fmt, ...);
@@ -73,4 +74,5 @@ struct DeviceGuard {
 // bank.cu / gcc_phat.cu clean-up hooks
 void frt_bank_release(frt_ctx *h);
 void frt_gcc_release(frt_ctx *h);
+void frt_dec_release(frt_ctx *h);
 int frt_pipe_ensure(frt_ctx *h, size_t in_bytes, size_t out_bytes);

@@ -129,6 +129,15 @@ int frt_gcc_phat(frt_handle h, const float *d0_dev, const float *d1_dev, int64_t
                  int n_pairs, float *xcorr_dev, float *smoothed_dev, int have_prev, int *idx_dev,
                  float *val_dev, void *stream);
 
+/* ---------------------------------------------------------------- N-fold decimation
+ * Stands behind `decimate_multiple(Ndec, bdec, adec, x, zis)` (friture/signal/decimate.py:45-71),
+ * the 48 kHz -> 12 kHz pre-stage of the delay estimator (friture/delay_estimator.py:53-59,97-98):
+ * n_stages x (order-12 elliptic low-pass as 6 float32 sections, keep even samples), state carried
+ * across calls.  n_samples % 256 == 0; out holds n_samples >> n_stages samples per channel.      */
+int frt_decimate_plan(frt_handle h, int n_channels, int n_stages, const double *sos_dec);
+int frt_decimate_process(frt_handle h, const float *x_dev, int64_t x_stride, int64_t n_samples,
+                         float *out_dev, int64_t out_stride, void *stream);
+
 /* ---------------------------------------------------------------- spectrum widget reductions
  * The per-tick numeric work of Spectrum_Widget.handle_new_data behind the STFT
  * (friture/spectrum.py:158-181): smoothing across the tick's frames
