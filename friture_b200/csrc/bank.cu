@@ -77,7 +77,9 @@ __device__ __forceinline__ long long y_offset(int k, int bpo, int n_oct, long lo
     return off + (long long)i * (t_total >> jk);
 }
 
-struct WarpCtx {
+template <bool WANT_Y>
+struct WarpCtxT {
+    static constexpr bool kWantY = WANT_Y;   // compile the ragged-y stores in or out
     const BankParams *P;
     float *s_z;       // [n_oct][nsec][2]   this warp's filter state (shared memory)
     float *s_e;       // [n_oct][bpo]       this warp's smoothing state (e / alpha form)
@@ -94,9 +96,9 @@ struct WarpCtx {
 template <int L> struct Log2 { static constexpr int v = 1 + Log2<L / 2>::v; };
 template <> struct Log2<1> { static constexpr int v = 0; };
 
-template <int L>
+template <int L, class W>
 __device__ __forceinline__ void section_scan(const float (&in)[L], float (&out)[L],
-                                             const WarpCtx &w, int j, int sec) {
+                                             const W &w, int j, int sec) {
     const BankParams &P = *w.P;
     const float b0 = P.coef[sec][0], b1 = P.coef[sec][1], b2 = P.coef[sec][2];
     const float a1 = P.coef[sec][3], a2 = P.coef[sec][4];
@@ -150,12 +152,12 @@ __device__ __forceinline__ void section_scan(const float (&in)[L], float (&out)[
     }
 }
 
-template <int N> __device__ void serial_stage(float xin, const WarpCtx &w, int j);
+template <class W> __device__ __forceinline__ void serial_stages(float xin, int n, const W &w, int j);
 
 // Band chains of one scan-mode stage (bands bpo-1 .. 0, friture/filter.py:105) with the smoothing
 // of y^2: L samples per lane, 32 lanes active.
-template <int L>
-__device__ __forceinline__ void bands_of_stage(const float (&xc)[L], const WarpCtx &w, int j) {
+template <int L, class W>
+__device__ __forceinline__ void bands_of_stage(const float (&xc)[L], const W &w, int j) {
     const BankParams &P = *w.P;
     const int bpo = P.bpo;
     float wk[L];
@@ -163,7 +165,7 @@ __device__ __forceinline__ void bands_of_stage(const float (&xc)[L], const WarpC
         section_scan<L>(xc, wk, w, j, 2 * i);
         section_scan<L>(wk, wk, w, j, 2 * i + 1);
         const int kband = (P.n_oct - 1 - j) * bpo + i;
-        if (w.y) {
+        if constexpr (W::kWantY) {
             float *yp = w.y + y_offset(kband, bpo, P.n_oct, w.t_total) + (w.t_off >> j) +
                         w.lane * L;
 #pragma unroll
@@ -192,8 +194,8 @@ __device__ __forceinline__ void bands_of_stage(const float (&xc)[L], const WarpC
 
 // Decimation low-pass of one scan-mode stage: 6 sections, full-rate output in wk
 // (the caller keeps the even samples, friture/signal/decimate.py:39-41).
-template <int L>
-__device__ __forceinline__ void dec_of_stage(const float (&xc)[L], float (&wk)[L], const WarpCtx &w,
+template <int L, class W>
+__device__ __forceinline__ void dec_of_stage(const float (&xc)[L], float (&wk)[L], const W &w,
                                              int j) {
     const int bpo = w.P->bpo;
     section_scan<L>(xc, wk, w, j, 2 * bpo);
@@ -202,8 +204,8 @@ __device__ __forceinline__ void dec_of_stage(const float (&xc)[L], float (&wk)[L
 }
 
 // One scan-mode stage, single-warp variant: bands, then the decimator, then the next stage.
-template <int L>
-__device__ void scan_stage(const float (&xc)[L], const WarpCtx &w, int j) {
+template <int L, class W>
+__device__ void scan_stage(const float (&xc)[L], const W &w, int j) {
     const BankParams &P = *w.P;
     bands_of_stage<L>(xc, w, j);
     if (j + 1 >= P.n_oct) return;   // the last decimator's output is discarded (filter.py:113)
@@ -216,7 +218,7 @@ __device__ void scan_stage(const float (&xc)[L], const WarpCtx &w, int j) {
         scan_stage<L / 2>(xn, w, j + 1);
     } else {
         // L == 2: one sample per lane is left -> switch to lane = chain
-        serial_stage<32>(wk[0], w, j + 1);
+        serial_stages<W>(wk[0], 32, w, j + 1);
     }
 }
 
@@ -228,8 +230,8 @@ __device__ void scan_stage(const float (&xc)[L], const WarpCtx &w, int j) {
 // D and B stage by stage, __syncthreads() closes a tile.
 __device__ __forceinline__ void bar_db() { asm volatile("bar.sync 1, 64;" ::: "memory"); }
 
-template <int L>
-__device__ void stage_D(const float (&xc)[L], const WarpCtx &w, int j, float *s_x, float *s_x32) {
+template <int L, class W>
+__device__ void stage_D(const float (&xc)[L], const W &w, int j, float *s_x, float *s_x32) {
     float wk[L];
     dec_of_stage<L>(xc, wk, w, j);
     if constexpr (L >= 4) {
@@ -248,8 +250,8 @@ __device__ void stage_D(const float (&xc)[L], const WarpCtx &w, int j, float *s_
     }
 }
 
-template <int L>
-__device__ void stage_B(const float (&xc)[L], const WarpCtx &w, int j, const float *s_x) {
+template <int L, class W>
+__device__ void stage_B(const float (&xc)[L], const W &w, int j, const float *s_x) {
     bands_of_stage<L>(xc, w, j);
     bar_db();
     if constexpr (L >= 4) {
@@ -261,76 +263,81 @@ __device__ void stage_B(const float (&xc)[L], const WarpCtx &w, int j, const flo
     }
 }
 
-// Serial-mode stage: N samples, sample m in lane m.  Lane r < bpo runs band chain r (2
-// sections), lane bpo runs the decimator chain (6 sections).
-template <int N>
-__device__ void serial_stage(float xin, const WarpCtx &w, int j) {
+// Serial-mode stages: the n samples of stage j sit one per lane (sample m in lane m).  Lane
+// r < bpo runs band chain r (2 sections), lane bpo runs the decimator chain (6 sections); samples
+// are broadcast one by one.  Continues through the remaining stages (n halves every stage).  One
+// rolled copy of this code serves all low-rate stages: instruction-cache footprint matters here.
+template <class W>
+__device__ __forceinline__ void serial_stages(float xin, int n, const W &w, int j) {
     const BankParams &P = *w.P;
     const int bpo = P.bpo, lane = w.lane;
-    const bool last = (j + 1 >= P.n_oct);
     const bool is_band = lane < bpo;
-    const bool is_dec = (lane == bpo) && !last;
-    const int nchain = is_band ? 2 : (is_dec ? 6 : 0);
-    const int sec0 = is_band ? 2 * lane : 2 * bpo;
-    const int nloop = last ? 2 : 6;
-    float z1[6], z2[6], cb0[6], cb1[6], cb2[6], ca1[6], ca2[6];
-#pragma unroll
-    for (int s = 0; s < 6; s++) {
-        const bool on = s < nchain;
-        const float *cf = w.s_coef + (sec0 + (on ? s : 0)) * 8;
-        cb0[s] = cf[0]; cb1[s] = cf[1]; cb2[s] = cf[2]; ca1[s] = cf[3]; ca2[s] = cf[4];
-        const float *zp = w.s_z + (j * P.nsec + sec0 + (on ? s : 0)) * 2;
-        z1[s] = zp[0];
-        z2[s] = zp[1];
-    }
-    const float q = P.qpow[j][0];
-    float e = is_band ? w.s_e[j * bpo + lane] : 0.f;
-    const int kband = (P.n_oct - 1 - j) * bpo + (is_band ? lane : 0);
-    float *yp = nullptr;
-    if (w.y && is_band)
-        yp = w.y + y_offset(kband, bpo, P.n_oct, w.t_total) + (w.t_off >> j);
-    float xnext = 0.f;
 #pragma unroll 1
-    for (int m = 0; m < N; m++) {   // rolled on purpose: instruction-cache footprint matters here
-        float v = __shfl_sync(0xffffffffu, xin, m);
+    for (; j < P.n_oct && n >= 1; j++, n >>= 1) {
+        const bool last = (j + 1 >= P.n_oct);
+        const bool is_dec = (lane == bpo) && !last;
+        const int nchain = is_band ? 2 : (is_dec ? 6 : 0);
+        const int sec0 = is_band ? 2 * lane : 2 * bpo;
+        float z1[6], z2[6], cb0[6], cb1[6], cb2[6], ca1[6], ca2[6];
 #pragma unroll
         for (int s = 0; s < 6; s++) {
-            if (s < nloop && s < nchain) {
-                const float y = fmaf(cb0[s], v, z1[s]);
-                z1[s] = fmaf(-ca1[s], y, fmaf(cb1[s], v, z2[s]));
-                z2[s] = fmaf(-ca2[s], y, cb2[s] * v);
-                v = y;
+            const bool on = s < nchain;
+            const float *cf = w.s_coef + (sec0 + (on ? s : 0)) * 8;
+            cb0[s] = cf[0]; cb1[s] = cf[1]; cb2[s] = cf[2]; ca1[s] = cf[3]; ca2[s] = cf[4];
+            const float *zp = w.s_z + (j * P.nsec + sec0 + (on ? s : 0)) * 2;
+            z1[s] = zp[0];
+            z2[s] = zp[1];
+        }
+        const float q = P.qpow[j][0];
+        float e = is_band ? w.s_e[j * bpo + lane] : 0.f;
+        const int kband = (P.n_oct - 1 - j) * bpo + (is_band ? lane : 0);
+        float *yp = nullptr;
+        if constexpr (W::kWantY) {
+            if (is_band) yp = w.y + y_offset(kband, bpo, P.n_oct, w.t_total) + (w.t_off >> j);
+        }
+        float xnext = 0.f;
+#pragma unroll 1
+        for (int m = 0; m < n; m++) {
+            float v = __shfl_sync(0xffffffffu, xin, m);
+#pragma unroll
+            for (int s = 0; s < 6; s++) {
+                if (s < nchain) {
+                    const float y = fmaf(cb0[s], v, z1[s]);
+                    z1[s] = fmaf(-ca1[s], y, fmaf(cb1[s], v, z2[s]));
+                    z2[s] = fmaf(-ca2[s], y, cb2[s] * v);
+                    v = y;
+                }
+            }
+            if (is_band) {
+                e = fmaf(e, q, v * v);
+                if constexpr (W::kWantY) {
+                    if (yp) yp[m] = v;
+                }
+            }
+            if ((m & 1) == 0) {   // keep even samples (friture/signal/decimate.py:41)
+                const float o = __shfl_sync(0xffffffffu, v, bpo);
+                if (lane == (m >> 1)) xnext = o;
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int s = 0; s < 6; s++) {
+            if (s < nchain) {
+                float *zp = w.s_z + (j * P.nsec + sec0 + s) * 2;
+                zp[0] = z1[s];
+                zp[1] = z2[s];
             }
         }
         if (is_band) {
-            e = fmaf(e, q, v * v);
-            if (yp) yp[m] = v;
+            w.s_e[j * bpo + lane] = e;
+            if (w.energies) w.energies[kband] = energy_out(P.alpha[j] * e, w.db);
         }
-        if (!last && (m & 1) == 0) {
-            const float o = __shfl_sync(0xffffffffu, v, bpo);
-            if (lane == (m >> 1)) xnext = o;
-        }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int s = 0; s < 6; s++) {
-        if (s < nchain) {
-            float *zp = w.s_z + (j * P.nsec + sec0 + s) * 2;
-            zp[0] = z1[s];
-            zp[1] = z2[s];
-        }
-    }
-    if (is_band) {
-        w.s_e[j * bpo + lane] = e;
-        if (w.energies) w.energies[kband] = energy_out(P.alpha[j] * e, w.db);
-    }
-    __syncwarp();
-    if constexpr (N >= 2) {
-        if (!last) serial_stage<N / 2>(xnext, w, j + 1);
+        __syncwarp();
+        xin = xnext;
     }
 }
 
-template <int L0>
+template <int L0, bool WANT_Y>
 __global__ void __launch_bounds__(64)
 bank_kernel(const __grid_constant__ BankParams P, const BankArgs a) {
     extern __shared__ float smem[];
@@ -355,7 +362,7 @@ bank_kernel(const __grid_constant__ BankParams P, const BankArgs a) {
 
     constexpr int TILE = 32 * L0;
     const int nbands = P.n_oct * P.bpo;
-    WarpCtx w;
+    WarpCtxT<WANT_Y> w;
     w.P = &P;
     w.s_z = s_z;
     w.s_e = s_e;
@@ -394,7 +401,7 @@ bank_kernel(const __grid_constant__ BankParams P, const BankArgs a) {
     for (int i = lane; i < ne; i += 32) ge[i] = s_e[i];
 }
 
-template <int L0>
+template <int L0, bool WANT_Y>
 __global__ void __launch_bounds__(96)
 bank_kernel3(const __grid_constant__ BankParams P, const BankArgs a) {
     extern __shared__ float smem[];
@@ -416,7 +423,7 @@ bank_kernel3(const __grid_constant__ BankParams P, const BankArgs a) {
     }
     __syncthreads();
     const int nbands = P.n_oct * P.bpo;
-    WarpCtx w;
+    WarpCtxT<WANT_Y> w;
     w.P = &P;
     w.s_z = s_z;
     w.s_e = s_e;
@@ -456,7 +463,7 @@ bank_kernel3(const __grid_constant__ BankParams P, const BankArgs a) {
                              ? a.energies + ((size_t)c * n_blocks + tp / a.tiles_per_block) * nbands
                              : nullptr;
             w.t_off = (long long)tp * TILE;
-            if (NSCAN < P.n_oct) serial_stage<32>(s_x32[(tp & 1) * 32 + lane], w, NSCAN);
+            if (NSCAN < P.n_oct) serial_stages<WarpCtxT<WANT_Y>>(s_x32[(tp & 1) * 32 + lane], 32, w, NSCAN);
         }
         __syncthreads();
     }
@@ -479,8 +486,8 @@ struct DecArgs {
     float *zstate;   // [C][n_stages][6][2]
 };
 
-template <int L>
-__device__ void dec_chain(const float (&xc)[L], const WarpCtx &w, int j, int n_stages, float *dst) {
+template <int L, class W>
+__device__ void dec_chain(const float (&xc)[L], const W &w, int j, int n_stages, float *dst) {
     float wk[L];
     dec_of_stage<L>(xc, wk, w, j);
     if (j + 1 == n_stages) {
@@ -508,7 +515,7 @@ decimate_kernel(const __grid_constant__ BankParams P, const DecArgs a) {
     float *gz = a.zstate + (size_t)c * nz;
     for (int i = lane; i < nz; i += 32) s_z[i] = gz[i];
     __syncwarp();
-    WarpCtx w;
+    WarpCtxT<false> w;
     w.P = &P;
     w.s_z = s_z;
     w.s_e = nullptr;
@@ -674,33 +681,38 @@ extern "C" int frt_bank_set_state(frt_handle h, const float *z_host, const float
     return FRT_OK;
 }
 
-template <int L0>
+template <int L0, bool WANT_Y>
 static cudaError_t launch_bank3(const BankPlan *pl, const BankArgs &a, cudaStream_t st) {
     const BankParams &P = pl->params;
     const size_t smem = sizeof(float) * ((size_t)P.nsec * 8 + pl->nz + pl->ne + 32 * L0 + 64);
-    cudaError_t e = cudaFuncSetAttribute(bank_kernel3<L0>,
+    cudaError_t e = cudaFuncSetAttribute(bank_kernel3<L0, WANT_Y>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    bank_kernel3<L0><<<(unsigned)a.n_channels, 96, smem, st>>>(P, a);
+    bank_kernel3<L0, WANT_Y><<<(unsigned)a.n_channels, 96, smem, st>>>(P, a);
+    return cudaGetLastError();
+}
+
+template <int L0, bool WANT_Y>
+static cudaError_t launch_bank_y(const BankPlan *pl, const BankArgs &a, cudaStream_t st) {
+    // few channels: three warps per channel (latency-bound regime); many channels: one warp
+    // per channel already saturates the schedulers with less synchronisation
+    static const char *force = getenv("FRT_BANK_WARPS");
+    const bool three = force ? (force[0] == '3') : (a.n_channels < 6144 && L0 <= 16);
+    if (three) return launch_bank3<L0, WANT_Y>(pl, a, st);
+    const BankParams &P = pl->params;
+    const int warps = 2;
+    const size_t smem = sizeof(float) * ((size_t)P.nsec * 8 + (size_t)warps * (pl->nz + pl->ne));
+    cudaError_t e = cudaFuncSetAttribute(bank_kernel<L0, WANT_Y>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const unsigned blocks = (unsigned)((a.n_channels + warps - 1) / warps);
+    bank_kernel<L0, WANT_Y><<<blocks, warps * 32, smem, st>>>(P, a);
     return cudaGetLastError();
 }
 
 template <int L0>
 static cudaError_t launch_bank(const BankPlan *pl, const BankArgs &a, cudaStream_t st) {
-    // few channels: three warps per channel (latency-bound regime); many channels: one warp
-    // per channel already saturates the schedulers with less synchronisation
-    static const char *force = getenv("FRT_BANK_WARPS");
-    const bool three = force ? (force[0] == '3') : (a.n_channels < 6144);
-    if (three) return launch_bank3<L0>(pl, a, st);
-    const BankParams &P = pl->params;
-    const int warps = 2;
-    const size_t smem = sizeof(float) * ((size_t)P.nsec * 8 + (size_t)warps * (pl->nz + pl->ne));
-    cudaError_t e = cudaFuncSetAttribute(bank_kernel<L0>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    const unsigned blocks = (unsigned)((a.n_channels + warps - 1) / warps);
-    bank_kernel<L0><<<blocks, warps * 32, smem, st>>>(P, a);
-    return cudaGetLastError();
+    return a.y ? launch_bank_y<L0, true>(pl, a, st) : launch_bank_y<L0, false>(pl, a, st);
 }
 
 extern "C" int frt_bank_process(frt_handle h, const float *x_dev, int64_t x_stride, int block,
