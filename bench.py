@@ -400,6 +400,19 @@ def other_workloads(args, dev, rank, world, barrier):
         ms_g = timed(stft_and_gather, 3)
         ms_s = timed(lambda: proc.stft(xs, hop=HOP, log=True, out=outc), 3)
         recv = outc.numel() * 4 * (world - 1)
+        # the same gather after the spectrum widget's per-tick reduction (one smoothed column per
+        # channel per tick instead of one per frame): the payload shrinks by the frames per tick
+        from friture_b200.spectrum import SpectrumAnalyzer
+        an = SpectrumAnalyzer(C, fft_size=N_FFT, overlap=0.5, response_time=0.125)
+        full_tick = torch.empty((C * world, NBINS), dtype=torch.float32, device=dev)
+
+        def tick_and_gather():
+            db, _, _ = an.process(xs)
+            allgather_channels(db, C * world, out=full_tick)
+        ms_t = timed(tick_and_gather, 3)
+        res["spectrum_tick_with_allgather"] = {"channels_per_gpu": C, "frames_per_tick": nblk - 1,
+                                               "ms": ms_t,
+                                               "spectra_per_s": C * (nblk - 1) * world / (ms_t * 1e-3)}
         res["stft_with_allgather"] = {"channels_per_gpu": C, "frames": nblk - 1, "ms_stft": ms_s,
                                       "ms_stft_plus_allgather": ms_g,
                                       "spectra_per_s": C * (nblk - 1) * world / (ms_g * 1e-3),
