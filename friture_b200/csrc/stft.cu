@@ -18,6 +18,7 @@
 // Generic path (every other size 32..16384): one CTA per frame, Stockham radix-4 (+ one radix-2
 //   pass when log2(M) is odd) ping-ponging between two shared-memory buffers.
 #include <cmath>
+#include <cstdlib>
 
 #include "frt_internal.cuh"
 
@@ -161,6 +162,44 @@ __device__ __forceinline__ float finish(float mag2, float scale) {
     return kLog10Scale * lg2_fast(fmaf(mag2, scale, kEps));
 }
 
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers ------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) {
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy by the TMA engine, completion signalled on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes,
+                                         unsigned long long *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
 // ------------------------------------------------------------------------------------------
 // Fast path, N = 2048.
 constexpr int FAST_N = 2048;
@@ -172,7 +211,8 @@ constexpr int FAST_WARPS = FRT_STFT_WARPS;
 constexpr int FAST_TILE = 32 * 33;   // padded 32x32 complex tile per warp
 constexpr int FAST_POST = 17 * 32;
 constexpr size_t FAST_SMEM =
-    sizeof(float2) * (FAST_M + FAST_M + FAST_POST + (size_t)FAST_WARPS * FAST_TILE);
+    sizeof(float2) * (FAST_M + FAST_M + FAST_POST + (size_t)FAST_WARPS * FAST_TILE) +
+    sizeof(unsigned long long) * FAST_WARPS;
 
 template <int MODE, int VEC>
 __global__ void __launch_bounds__(FAST_WARPS * 32, 1)
@@ -187,7 +227,9 @@ stft2048_kernel(const float *__restrict__ x, long long x_stride, long long n_fra
     float2 *s_post = s_tw + FAST_M;       // [17][32] U[t + 32 m] = -j W_2048^(t+32m)
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    float2 *s_x = s_post + FAST_POST + warp * FAST_TILE;
+    float2 *s_x = s_post + FAST_POST + warp * FAST_TILE;   // 16-byte aligned: FAST_TILE*8 % 16 == 0
+    unsigned long long *s_bar =
+        reinterpret_cast<unsigned long long *>(s_post + FAST_POST + FAST_WARPS * FAST_TILE);
 
     for (int i = threadIdx.x; i < FAST_M; i += blockDim.x) {
         s_win[i] = win2[i];
@@ -206,6 +248,21 @@ stft2048_kernel(const float *__restrict__ x, long long x_stride, long long n_fra
     if (item_end > total_items) item_end = total_items;
     const float scale = 1.0f / (4.0f * (float)FAST_N * (float)FAST_N);
     const int src_lane = (32 - lane) & 31;
+    // VEC == 2: the next frame's 8 KB of samples are fetched by the TMA engine (cp.async.bulk)
+    // into this warp's exchange tile while the current frame is in its second FFT pass and split
+    // step, so no warp ever waits on a global load with its registers tied up.
+    unsigned long long *bar = s_bar + warp;
+    unsigned parity = 0;
+    if (VEC == 2) {
+        if (lane == 0) mbar_init(bar, 1);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0 && item < item_end) {
+            mbar_expect_tx(bar, FAST_N * 4);
+            bulk_g2s(s_x, x + (item / n_frames) * x_stride + (item % n_frames) * hop, FAST_N * 4,
+                     bar);
+        }
+    }
 #if FRT_STFT_WINDOW_ON_THE_FLY
     // Hann window w[n] = 0.5 - 0.5 cos(theta n), theta = 2 pi/(N-1), n = 64 n1 + 2 t + e:
     // cos(theta n) = cos(A) cos(B) - sin(A) sin(B) with A = 64 theta n1 (compile-time constants in
@@ -221,7 +278,13 @@ stft2048_kernel(const float *__restrict__ x, long long x_stride, long long n_fra
     for (; item < item_end; item++) {
         const float *p = x + c * x_stride + f * hop;
         float2 v[32];
-        if (VEC) {
+        if (VEC == 2) {
+            mbar_wait(bar, parity);
+            parity ^= 1;
+#pragma unroll
+            for (int n1 = 0; n1 < 32; n1++) v[n1] = s_x[32 * n1 + lane];
+            __syncwarp();   // every lane has its samples before the tile is reused for the exchange
+        } else if (VEC) {
             const float2 *p2 = reinterpret_cast<const float2 *>(p);
 #pragma unroll
             for (int n1 = 0; n1 < 32; n1++) v[n1] = __ldg(p2 + 32 * n1 + lane);
@@ -256,6 +319,18 @@ stft2048_kernel(const float *__restrict__ x, long long x_stride, long long n_fra
 #pragma unroll
         for (int n2 = 0; n2 < 32; n2++) v[n2] = s_x[lane * 33 + n2];
         __syncwarp();
+        if (VEC == 2 && item + 1 < item_end) {   // tile is free: prefetch the next frame into it
+            long long cn = c, fn = f + 1;
+            if (fn == n_frames) {
+                fn = 0;
+                cn++;
+            }
+            fence_proxy_async();
+            if (lane == 0) {
+                mbar_expect_tx(bar, FAST_N * 4);
+                bulk_g2s(s_x, x + cn * x_stride + fn * hop, FAST_N * 4, bar);
+            }
+        }
         dft32(v);   // v[r] = Z[lane + 32*brev5(r)]
 
         float *o = out + c * out_stride_c + f * out_stride_f;
@@ -391,8 +466,10 @@ cudaError_t set_fast_smem_one() {
 cudaError_t set_fast_smem() {
     cudaError_t e = set_fast_smem_one<0, 0>();
     if (e == cudaSuccess) e = set_fast_smem_one<0, 1>();
+    if (e == cudaSuccess) e = set_fast_smem_one<0, 2>();
     if (e == cudaSuccess) e = set_fast_smem_one<1, 0>();
     if (e == cudaSuccess) e = set_fast_smem_one<1, 1>();
+    if (e == cudaSuccess) e = set_fast_smem_one<1, 2>();
     return e;
 }
 
@@ -505,18 +582,23 @@ extern "C" int frt_stft_process(frt_handle h, const float *x_dev, int64_t x_stri
     const long long total = (long long)n_channels * n_frames;
     cudaStream_t st = (cudaStream_t)stream;
     if (pl.n_fft == FAST_N) {
-        const int vec_ok = (((uintptr_t)x_dev & 7) == 0) && ((x_stride & 1) == 0) &&
-                           ((hop & 1) == 0);
+        int vec_ok = (((uintptr_t)x_dev & 7) == 0) && ((x_stride & 1) == 0) && ((hop & 1) == 0);
+        // 16-byte aligned frames: let the TMA engine stage them (cp.async.bulk)
+        static const int no_tma = getenv("FRT_STFT_NO_TMA") ? 1 : 0;   // tuning knob
+        if (!no_tma && (((uintptr_t)x_dev & 15) == 0) && ((x_stride & 3) == 0) && ((hop & 3) == 0))
+            vec_ok = 2;
         long long blocks = (total + FAST_WARPS - 1) / FAST_WARPS;
         if (blocks > h->sm_count) blocks = h->sm_count;
 #define FRT_LAUNCH_FAST(MODE, VEC)                                                         \
     launch_fast<MODE, VEC>((unsigned)blocks, st, x_dev, x_stride, n_frames, hop, out_dev,   \
                            out_stride_c, out_stride_f, pl, total)
         if (mode == FRT_STFT_POWER) {
-            if (vec_ok) FRT_LAUNCH_FAST(FRT_STFT_POWER, 1);
+            if (vec_ok == 2) FRT_LAUNCH_FAST(FRT_STFT_POWER, 2);
+            else if (vec_ok) FRT_LAUNCH_FAST(FRT_STFT_POWER, 1);
             else FRT_LAUNCH_FAST(FRT_STFT_POWER, 0);
         } else {
-            if (vec_ok) FRT_LAUNCH_FAST(FRT_STFT_LOGPOWER, 1);
+            if (vec_ok == 2) FRT_LAUNCH_FAST(FRT_STFT_LOGPOWER, 2);
+            else if (vec_ok) FRT_LAUNCH_FAST(FRT_STFT_LOGPOWER, 1);
             else FRT_LAUNCH_FAST(FRT_STFT_LOGPOWER, 0);
         }
 #undef FRT_LAUNCH_FAST
