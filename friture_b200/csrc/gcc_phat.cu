@@ -18,13 +18,14 @@
 
 namespace {
 
-constexpr int GCC_THREADS = 1024;
+constexpr int GCC_THREADS = 512;
 constexpr int GCC_MAX_PASSES = 16;
-constexpr int GCC_MAX_PER_THREAD = 16;   // (L/2+1) / GCC_THREADS rounded up must not exceed this
+constexpr int GCC_MAX_PER_THREAD = 28;   // (L/2+1) / GCC_THREADS rounded up must not exceed this
 
 struct GccRadices {
     int n_passes;
     int radix[GCC_MAX_PASSES];
+    unsigned magic[GCC_MAX_PASSES];   // ceil(2^32 / n_next) of the pass: idx / n_next == umulhi(idx, magic)
 };
 
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
@@ -75,19 +76,67 @@ template <> __device__ __forceinline__ void dft<5>(float2 (&v)[5]) {
     v[3] = csub(t2, u2);
 }
 
+#include "unit_roots.inc"
+
+// Composite in-register DFT of R = R1*R2 points: R2 DFTs of size R1 over the stride-R2 sub-
+// sequences, twiddles W_R^(q2 k1) (compile-time constants), R1 DFTs of size R2;
+// V[k1 + R1 k2] = sum_q v[q] W_R^(q k), q = q1 R2 + q2.
+template <int R1, int R2>
+__device__ __forceinline__ void dft_comp(float2 (&v)[R1 * R2]) {
+    constexpr int R = R1 * R2;
+#pragma unroll
+    for (int q2 = 0; q2 < R2; q2++) {
+        float2 t[R1];
+#pragma unroll
+        for (int q1 = 0; q1 < R1; q1++) t[q1] = v[q1 * R2 + q2];
+        dft<R1>(t);
+#pragma unroll
+        for (int k1 = 0; k1 < R1; k1++) {
+            const int m = q2 * k1;
+            v[k1 * R2 + q2] = (m == 0) ? t[k1]
+                                       : cmul(t[k1], make_float2(UnitRoots<R>::c(m), -UnitRoots<R>::s(m)));
+        }
+    }
+    float2 o[R];
+#pragma unroll
+    for (int k1 = 0; k1 < R1; k1++) {
+        float2 t[R2];
+#pragma unroll
+        for (int q2 = 0; q2 < R2; q2++) t[q2] = v[k1 * R2 + q2];
+        dft<R2>(t);
+#pragma unroll
+        for (int k2 = 0; k2 < R2; k2++) o[k1 + R1 * k2] = t[k2];
+    }
+#pragma unroll
+    for (int k = 0; k < R; k++) v[k] = o[k];
+}
+template <> __device__ __forceinline__ void dft<16>(float2 (&v)[16]) { dft_comp<4, 4>(v); }
+template <> __device__ __forceinline__ void dft<25>(float2 (&v)[25]) { dft_comp<5, 5>(v); }
+template <> __device__ __forceinline__ void dft<15>(float2 (&v)[15]) { dft_comp<3, 5>(v); }
+
 // One in-place DIF pass of radix R on sub-transforms of length n (n_next = n / R).
-template <int R>
-__device__ __forceinline__ void dif_pass(float2 *z, int L, int n, const float2 *__restrict__ tw) {
+// FIRST: the pass also applies (x - mean) * hanning on its loads (correlation.py:27-31), so the
+// windowing costs no extra sweep over shared memory.
+template <int R, bool FIRST>
+__device__ __forceinline__ void dif_pass(float2 *z, int L, int n, unsigned magic,
+                                         const float2 *__restrict__ tw,
+                                         const float *__restrict__ window, float m0, float m1) {
     const int n_next = n / R;
     const int tw_step = L / n;
     const int total = L / R;
     for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-        const int blk = idx / n_next;
+        const int blk = (n_next == 1) ? idx : (int)__umulhi((unsigned)idx, magic);
         const int j = idx - blk * n_next;
         float2 *p = z + blk * n + j;
         float2 v[R];
 #pragma unroll
-        for (int q = 0; q < R; q++) v[q] = p[q * n_next];
+        for (int q = 0; q < R; q++) {
+            v[q] = p[q * n_next];
+            if (FIRST) {
+                const float w = __ldg(window + blk * n + j + q * n_next);
+                v[q] = make_float2((v[q].x - m0) * w, (v[q].y - m1) * w);
+            }
+        }
         dft<R>(v);
         p[0] = v[0];
         // W_n^(j q), q = 1..R-1: one table read, the rest by successive products
@@ -102,14 +151,28 @@ __device__ __forceinline__ void dif_pass(float2 *z, int L, int n, const float2 *
     }
 }
 
-__device__ __noinline__ void fft_inplace(float2 *z, int L, const GccRadices &rd, const float2 *__restrict__ tw) {
+template <bool FIRST>
+__device__ __forceinline__ void run_pass(int r, float2 *z, int L, int n, unsigned magic,
+                                         const float2 *__restrict__ tw,
+                                         const float *__restrict__ window, float m0, float m1) {
+    if (r == 16) dif_pass<16, FIRST>(z, L, n, magic, tw, window, m0, m1);
+    else if (r == 25) dif_pass<25, FIRST>(z, L, n, magic, tw, window, m0, m1);
+    else if (r == 15) dif_pass<15, FIRST>(z, L, n, magic, tw, window, m0, m1);
+    else if (r == 4) dif_pass<4, FIRST>(z, L, n, magic, tw, window, m0, m1);
+    else if (r == 5) dif_pass<5, FIRST>(z, L, n, magic, tw, window, m0, m1);
+    else if (r == 3) dif_pass<3, FIRST>(z, L, n, magic, tw, window, m0, m1);
+    else dif_pass<2, FIRST>(z, L, n, magic, tw, window, m0, m1);
+}
+
+// In-place FFT; when `window` is given the first pass also removes the means and applies it.
+__device__ __noinline__ void fft_inplace(float2 *z, int L, const GccRadices &rd,
+                                         const float2 *__restrict__ tw,
+                                         const float *__restrict__ window, float m0, float m1) {
     int n = L;
     for (int i = 0; i < rd.n_passes; i++) {
         const int r = rd.radix[i];
-        if (r == 4) dif_pass<4>(z, L, n, tw);
-        else if (r == 5) dif_pass<5>(z, L, n, tw);
-        else if (r == 3) dif_pass<3>(z, L, n, tw);
-        else dif_pass<2>(z, L, n, tw);
+        if (i == 0 && window) run_pass<true>(r, z, L, n, rd.magic[i], tw, window, m0, m1);
+        else run_pass<false>(r, z, L, n, rd.magic[i], tw, window, m0, m1);
         n /= r;
         __syncthreads();
     }
@@ -206,13 +269,7 @@ __global__ void __launch_bounds__(GCC_THREADS, 1) gcc_phat_kernel(const GccArgs 
             __syncthreads();
             continue;
         }
-        for (int n = tid; n < L; n += nt) {
-            const float w = __ldg(a.window + n);
-            const float2 v = z[n];
-            z[n] = make_float2((v.x - m0) * w, (v.y - m1) * w);
-        }
-        __syncthreads();
-        fft_inplace(z, L, a.rd, a.tw);
+        fft_inplace(z, L, a.rd, a.tw, a.window, m0, m1);   // mean removal + window fused in
 
         // G[k] = conj(D0[k]) D1[k], k = 0..L/2, kept in registers
         float2 g[GCC_MAX_PER_THREAD];
@@ -247,7 +304,7 @@ __global__ void __launch_bounds__(GCC_THREADS, 1) gcc_phat_kernel(const GccArgs 
             }
         }
         __syncthreads();
-        fft_inplace(z, L, a.rd, a.tw);
+        fft_inplace(z, L, a.rd, a.tw, nullptr, 0.f, 0.f);
 
         // smoothing (delay_estimator.py:134-139) and arg-max of |Xs| (first maximum wins)
         const float inv = 1.0f / (float)L;
@@ -339,12 +396,25 @@ extern "C" int frt_gcc_plan(frt_handle h, int length) {
     GccRadices rd;
     rd.n_passes = 0;
     int n = length;
-    while (n % 4 == 0) { rd.radix[rd.n_passes++] = 4; n /= 4; }
-    while (n % 2 == 0) { rd.radix[rd.n_passes++] = 2; n /= 2; }
-    while (n % 5 == 0) { rd.radix[rd.n_passes++] = 5; n /= 5; }
-    while (n % 3 == 0) { rd.radix[rd.n_passes++] = 3; n /= 3; }
-    if (n != 1 || rd.n_passes > GCC_MAX_PASSES)
+    // large composite radices first (16 = 4x4, 25 = 5x5, 15 = 3x5 run in registers): every pass
+    // is a full sweep over the 8*L-byte shared-memory buffer
+    while (n % 16 == 0 && rd.n_passes < GCC_MAX_PASSES) { rd.radix[rd.n_passes++] = 16; n /= 16; }
+    while (n % 4 == 0 && rd.n_passes < GCC_MAX_PASSES) { rd.radix[rd.n_passes++] = 4; n /= 4; }
+    while (n % 2 == 0 && rd.n_passes < GCC_MAX_PASSES) { rd.radix[rd.n_passes++] = 2; n /= 2; }
+    while (n % 25 == 0 && rd.n_passes < GCC_MAX_PASSES) { rd.radix[rd.n_passes++] = 25; n /= 25; }
+    while (n % 15 == 0 && rd.n_passes < GCC_MAX_PASSES) { rd.radix[rd.n_passes++] = 15; n /= 15; }
+    while (n % 5 == 0 && rd.n_passes < GCC_MAX_PASSES) { rd.radix[rd.n_passes++] = 5; n /= 5; }
+    while (n % 3 == 0 && rd.n_passes < GCC_MAX_PASSES) { rd.radix[rd.n_passes++] = 3; n /= 3; }
+    if (n != 1)
         return frt_fail(h, FRT_EINVAL, "length %d is not of the form 2^a 3^b 5^c", length);
+    {
+        int nn = length;
+        for (int i = 0; i < rd.n_passes; i++) {
+            const int n_next = nn / rd.radix[i];
+            rd.magic[i] = n_next > 1 ? (unsigned)((0x100000000ULL + n_next - 1) / n_next) : 0u;
+            nn = n_next;
+        }
+    }
     frt_gcc_release(h);
     GccPlan *pl = new (std::nothrow) GccPlan();
     if (!pl) return frt_fail(h, FRT_ENOMEM, "out of host memory");
