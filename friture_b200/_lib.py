@@ -69,6 +69,9 @@ SIGNATURES = {
                                     c_void_p]),
     "frt_decimate_plan": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "frt_decimate_process": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
+    "frt_display_columns": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_int,
+                                    c_void_p, c_float, c_float, c_void_p, c_void_p, c_int, c_void_p,
+                                    c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
 }
 
 _lib = None

@@ -122,3 +122,101 @@ extern "C" int frt_spectrum_reduce(frt_handle h, const float *power_dev, int64_t
     FRT_CUDA(h, cudaGetLastError());
     return FRT_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Spectrogram display chain: dB + weighting -> [0,1] scaling
+// (friture/spectrogram.py:127-129,161-162) -> frequency-axis interpolation to the screen rows
+// (np.interp on a Mel/Log/... grid, friture/signal/frequency_resampler.py:67-83) -> online linear
+// resampling along time to the screen columns (friture/signal/online_linear_2D_resampler.py:61-97,
+// friture/signal/linear_interp.py:11-62) -> clip + colour look-up lut[int(v*255)]
+// (friture/signal/color_tranform.py:48-51, friture/signal/lookup_table.py:32-52), one kernel.
+// The host works out which input column feeds which output column and with what weight (the
+// resampler's scalar bookkeeping); the kernel is one thread per output pixel.
+namespace {
+
+__device__ __forceinline__ float screen_value(const float *__restrict__ col,
+                                              const float *__restrict__ weight, int i0, float t,
+                                              float spec_min, float inv_range) {
+    // np.interp between bins i0 and i0+1 of (dB + w - spec_min) / (spec_max - spec_min)
+    float a = __ldg(col + i0), b = __ldg(col + i0 + 1);
+    if (weight) {
+        a += __ldg(weight + i0);
+        b += __ldg(weight + i0 + 1);
+    }
+    a = (a - spec_min) * inv_range;
+    b = (b - spec_min) * inv_range;
+    return fmaf(t, b - a, a);
+}
+
+__global__ void display_kernel(const float *__restrict__ db, long long stride_c, long long stride_f,
+                               int n_frames, const float *__restrict__ weight, float spec_min,
+                               float inv_range, const int *__restrict__ row_i0,
+                               const float *__restrict__ row_t, int height,
+                               const int *__restrict__ out_col, const float *__restrict__ out_a,
+                               int n_out, float *__restrict__ old_data,
+                               const unsigned *__restrict__ lut, unsigned *__restrict__ pixels) {
+    const int c = blockIdx.y;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)height * (n_out > 0 ? n_out : 1);
+    if (gid >= total) return;
+    const int r = (int)(gid / (n_out > 0 ? n_out : 1));
+    const int o = (int)(gid - (long long)r * (n_out > 0 ? n_out : 1));
+    const float *base = db + (size_t)c * stride_c;
+    const int i0 = __ldg(row_i0 + r);
+    const float t = __ldg(row_t + r);
+    if (n_out > 0) {
+        const int j = __ldg(out_col + o);       // input column this output column is drawn from
+        const float a = __ldg(out_a + o);       // weight of the previous input column
+        const float cur = screen_value(base + (size_t)j * stride_f, weight, i0, t, spec_min, inv_range);
+        const float old = (j > 0) ? screen_value(base + (size_t)(j - 1) * stride_f, weight, i0, t,
+                                                 spec_min, inv_range)
+                                  : old_data[(size_t)c * height + r];
+        float v = cur * (1.0f - a) + old * a;   // linear_interp.py:56-59
+        v = fminf(fmaxf(v, 0.f), 1.f);          // color_tranform.py:50
+        pixels[((size_t)c * height + r) * n_out + o] = __ldg(lut + (int)(v * 255.0f));
+    }
+    // carry the last column of this tick (online_linear_2D_resampler.py "shift"); one writer per row
+    // and only after every reader of the old value is done -> done by a second launch (n_out == 0)
+    if (n_out == 0 && n_frames > 0)
+        old_data[(size_t)c * height + r] =
+            screen_value(base + (size_t)(n_frames - 1) * stride_f, weight, i0, t, spec_min, inv_range);
+}
+
+}   // namespace
+
+extern "C" int frt_display_columns(frt_handle h, const float *db_dev, int64_t stride_c,
+                                   int64_t stride_f, int n_channels, int n_frames, int nbins,
+                                   const float *weight_dev, float spec_min, float spec_max,
+                                   const int *row_i0_dev, const float *row_t_dev, int height,
+                                   const int *out_col_dev, const float *out_a_dev, int n_out,
+                                   float *old_data_dev, const uint32_t *lut_dev,
+                                   uint32_t *pixels_dev, void *stream) {
+    if (!h) return FRT_EINVAL;
+    DeviceGuard g(h->device);
+    FRT_CHECK_ARG(h, n_channels >= 0 && n_frames >= 0 && height >= 1 && n_out >= 0 && nbins >= 2,
+                  "bad shape");
+    FRT_CHECK_ARG(h, spec_max != spec_min, "empty dB range");
+    if (n_channels == 0 || n_frames == 0) return FRT_OK;
+    FRT_CHECK_ARG(h, db_dev && row_i0_dev && row_t_dev && old_data_dev && lut_dev, "NULL buffer");
+    FRT_CHECK_ARG(h, n_out == 0 || (out_col_dev && out_a_dev && pixels_dev), "NULL output buffer");
+    const float inv_range = 1.0f / (spec_max - spec_min);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_out > 0) {
+        const long long total = (long long)height * n_out;
+        dim3 grid((unsigned)((total + 255) / 256), (unsigned)n_channels);
+        display_kernel<<<grid, 256, 0, st>>>(db_dev, stride_c, stride_f, n_frames, weight_dev,
+                                             spec_min, inv_range, row_i0_dev, row_t_dev, height,
+                                             out_col_dev, out_a_dev, n_out, old_data_dev,
+                                             reinterpret_cast<const unsigned *>(lut_dev),
+                                             reinterpret_cast<unsigned *>(pixels_dev));
+        h->launches++;
+    }
+    dim3 grid2((unsigned)((height + 255) / 256), (unsigned)n_channels);
+    display_kernel<<<grid2, 256, 0, st>>>(db_dev, stride_c, stride_f, n_frames, weight_dev, spec_min,
+                                          inv_range, row_i0_dev, row_t_dev, height, nullptr, nullptr,
+                                          0, old_data_dev, reinterpret_cast<const unsigned *>(lut_dev),
+                                          nullptr);
+    h->launches++;
+    FRT_CUDA(h, cudaGetLastError());
+    return FRT_OK;
+}

@@ -152,6 +152,24 @@ int frt_spectrum_reduce(frt_handle h, const float *power_dev, int64_t stride_c, 
                         const float *weight_dev, float *db_dev, int *fmax_idx_dev,
                         int *pitch_idx_dev, void *stream);
 
+/* ---------------------------------------------------------------- spectrogram display chain
+ * The Transform_Pipeline behind the spectrogram (friture/spectrogram.py:161-169): scaling of
+ * dB + weighting to [0,1] (spectrogram.py:127-129), Frequency_Resampler.push
+ * (friture/signal/frequency_resampler.py:67-83), Online_Linear_2D_resampler.push
+ * (friture/signal/online_linear_2D_resampler.py:61-97) and Color_Transform.push
+ * (friture/signal/color_tranform.py:48-51), fused.  The host supplies the screen-row table
+ * (row_i0/row_t: bin index and fraction of every screen row on the chosen frequency scale) and,
+ * per output column, the input column it is drawn from and the weight of the previous input
+ * column (the resampler's index bookkeeping).  db_dev [C][n_frames][nbins] log-power columns,
+ * old_data_dev [C][height] carried last column (in/out), lut_dev [256] 0xAARRGGBB,
+ * pixels_dev [C][height][n_out].                                                              */
+int frt_display_columns(frt_handle h, const float *db_dev, int64_t stride_c, int64_t stride_f,
+                        int n_channels, int n_frames, int nbins, const float *weight_dev,
+                        float spec_min, float spec_max, const int *row_i0_dev,
+                        const float *row_t_dev, int height, const int *out_col_dev,
+                        const float *out_a_dev, int n_out, float *old_data_dev,
+                        const uint32_t *lut_dev, uint32_t *pixels_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -336,3 +336,48 @@ class SpectrumWidgetOracle:
         i = int(np.argmax(db))
         pitch = int(np.argmax(harmonic_product_spectrum(sp)))
         return db, self.freq[i], max(self.freq[pitch], 1e-20), i, pitch
+
+
+# --------------------------------------------------------------------------- display chain
+def frequency_resample(data, freq, xscaled):
+    """Frequency_Resampler.push: np.interp per column (friture/signal/frequency_resampler.py:67-83).
+    data [bins, n] -> [len(xscaled), n]."""
+    out = np.zeros((len(xscaled), data.shape[1]))
+    for j in range(data.shape[1]):
+        out[:, j] = np.interp(xscaled, freq, data[:, j])
+    return out
+
+
+class OnlineLinear2DResamplerOracle:
+    """Online_Linear_2D_resampler (friture/signal/online_linear_2D_resampler.py:13-97 with
+    linear_interp_2D, friture/signal/linear_interp.py:11-62), height fixed."""
+
+    def __init__(self, interp_factor_L, decim_factor_M, height):
+        self.ratio = float(interp_factor_L) / decim_factor_M
+        self.orig_index = 0.
+        self.resampled_index = 0.
+        self.old_data = np.zeros(height)
+
+    def processable(self, m):
+        return int(np.ceil((self.orig_index + m - (self.resampled_index + self.ratio)) / self.ratio))
+
+    def push(self, data):
+        cols = []
+        for j in range(data.shape[1]):
+            self.orig_index += 1.
+            n = self.processable(0)
+            if n > 0:
+                new_indices = self.resampled_index + self.ratio * np.arange(1, n + 1, dtype=np.float64)
+                a = self.orig_index - new_indices
+                cols.append(data[:, j][:, None] * (1.0 - a)[None, :] + self.old_data[:, None] * a[None, :])
+                self.resampled_index = float(new_indices[-1])
+            self.old_data = data[:, j]
+        if not cols:
+            return np.zeros((data.shape[0], 0))
+        return np.concatenate(cols, axis=1)
+
+
+def color_transform(lut, data):
+    """Color_Transform.push: clip to [0,1], lut[int(v*255)]
+    (friture/signal/color_tranform.py:48-51, friture/signal/lookup_table.py:32-52)."""
+    return lut[(np.clip(data, 0., 1.) * 255).astype(np.intp)]

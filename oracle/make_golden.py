@@ -157,6 +157,36 @@ def main():
     np.savez_compressed(os.path.join(OUT, "exp_smoothing.npz"), data=data, prev=prev, alpha=alpha,
                         out=exp_smoothed_value_2d(kernel, alpha, data, prev))
 
+    # (vii) display chain: the reference's Frequency_Resampler and Online_Linear_2D_resampler on
+    #       three ticks of scaled dB columns (Mel grid, 20 Hz..24 kHz, 96 rows), then the colour LUT
+    #       (Color_Transform needs PyQt6's QColor; its .rgb() word is restated as
+    #       0xFF000000 | r<<16 | g<<8 | b on the reference's generated_cmrmap.CMAP)
+    from fractions import Fraction
+    import friture.plotting.frequency_scales as fscales
+    from friture.signal.frequency_resampler import Frequency_Resampler
+    from friture.signal.online_linear_2D_resampler import Online_Linear_2D_resampler
+    from friture.signal.lookup_table import color_from_float_2D
+    from friture.plotting import generated_cmrmap
+    cmap = generated_cmrmap.CMAP
+    lut = np.array([0xFF000000 | (int(c[0] * 255) << 16) | (int(c[1] * 255) << 8) | int(c[2] * 255)
+                    for c in cmap], dtype=np.uint32)
+    rng = np.random.default_rng(77)
+    nb, height = 1025, 96
+    freq = np.linspace(0, 24000, nb)
+    fr = Frequency_Resampler(fscales.Mel, 20., 24000., height)
+    fr.setfreq(freq)
+    L, M = Fraction(48000, 2048) / (Fraction(1) - Fraction(3, 4)) / 1000, Fraction(700, 10000)
+    tr = Online_Linear_2D_resampler(L, M, height)
+    d = {"lut": lut, "xscaled": fr.xscaled, "ratio": float(L) / float(M)}
+    for tick, ncols in enumerate((5, 1, 9)):
+        db = (-140.0 + 150.0 * rng.random((nb, ncols))).astype(np.float32)     # dB columns
+        norm = (db.astype(np.float64) - (-140.0)) / (0.0 - (-140.0))            # spectrogram.py:127-129
+        res = tr.push(fr.push(norm))
+        d["db_%d" % tick] = db
+        d["resampled_%d" % tick] = res
+        d["pixels_%d" % tick] = color_from_float_2D(lut, np.clip(res, 0., 1.))
+    np.savez_compressed(os.path.join(OUT, "display.npz"), **d)
+
     # coefficients carried over from the reference (pins friture_b200/data/filters.npz)
     d = {"bdec": bdec, "adec": adec}
     for bpo in (1, 3, 6, 12, 24):
