@@ -106,6 +106,7 @@ extern "C" int frt_destroy(frt_handle h) {
     if (h->stft.tw_dev) cudaFree(h->stft.tw_dev);
     if (h->stft.post_dev) cudaFree(h->stft.post_dev);
     if (h->stft.wlane_dev) cudaFree(h->stft.wlane_dev);
+    if (h->stft.comb_dev) cudaFree(h->stft.comb_dev);
     frt_bank_release(h);
     frt_gcc_release(h);
     frt_dec_release(h);

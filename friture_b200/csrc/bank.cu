@@ -770,15 +770,12 @@ struct DecPlan {
     float *zstate = nullptr;
 };
 
-static DecPlan *g_unused_decplan = nullptr;   // (plans live in the handle; see frt_ctx::dec)
-
 void frt_dec_release(frt_ctx *h) {
     DecPlan *pl = reinterpret_cast<DecPlan *>(h->dec);
     if (!pl) return;
     if (pl->zstate) cudaFree(pl->zstate);
     delete pl;
     h->dec = nullptr;
-    (void)g_unused_decplan;
 }
 
 extern "C" int frt_decimate_plan(frt_handle h, int n_channels, int n_stages, const double *sos_dec) {

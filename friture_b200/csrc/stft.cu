@@ -370,6 +370,128 @@ stft2048_kernel(const float *__restrict__ x, long long x_stride, long long n_fra
 }
 
 // ------------------------------------------------------------------------------------------
+// N = 4096 / 8192 (the spectrogram's and the spectrum's default sizes): R = 2 / 4 warps per frame.
+// Warp w runs the 1024-point complex FFT of the decimated sequence z[R n + w] exactly like the
+// N = 2048 kernel (radix-32 x 32 in registers, one transpose through its smem tile), leaves
+// Z_w[k0] in natural order in the tile, and after one block barrier the CTA combines
+//   Z[k0 + 1024 q] = sum_w W_R^(w q) W_M^(w k0) Z_w[k0]          (M = 1024 R)
+// and applies the real-FFT split step.  The partner of bin k0 + 1024 q is (1024 - k0) + 1024 (R-1-q),
+// so a thread that builds the groups of k0 and 1024 - k0 has all 2R bins it needs in registers.
+template <int R> __device__ __forceinline__ void combine(float2 (&t)[R]);
+template <> __device__ __forceinline__ void combine<2>(float2 (&t)[2]) {
+    const float2 a = t[0], b = t[1];
+    t[0] = cadd(a, b);
+    t[1] = csub(a, b);
+}
+template <> __device__ __forceinline__ void combine<4>(float2 (&t)[4]) {
+    const float2 s02 = cadd(t[0], t[2]), d02 = csub(t[0], t[2]);
+    const float2 s13 = cadd(t[1], t[3]), d13 = mul_mj(csub(t[1], t[3]));
+    t[0] = cadd(s02, s13);
+    t[1] = cadd(d02, d13);
+    t[2] = csub(s02, s13);
+    t[3] = csub(d02, d13);
+}
+
+template <int R>
+__device__ __forceinline__ void load_group(const float2 *__restrict__ tiles,
+                                           const float2 *__restrict__ comb, int k0,
+                                           float2 (&t)[R]) {
+    t[0] = tiles[k0];
+#pragma unroll
+    for (int w = 1; w < R; w++)
+        t[w] = cmul(tiles[w * FAST_TILE + k0], __ldg(comb + (w - 1) * 1024 + k0));
+    combine<R>(t);
+}
+
+template <int MODE>
+__device__ __forceinline__ void split_store(float *__restrict__ o, int kk, int M, float2 z, float2 zp,
+                                            const float2 *__restrict__ post, float scale) {
+    const float2 E = make_float2(z.x + zp.x, z.y - zp.y);
+    const float2 O = make_float2(z.x - zp.x, z.y + zp.y);
+    const float2 T = cmul(O, __ldg(post + kk));
+    const float2 X = cadd(E, T);
+    const float2 Y = csub(E, T);
+    o[kk] = finish<MODE>(fmaf(X.x, X.x, X.y * X.y), scale);
+    o[M - kk] = finish<MODE>(fmaf(Y.x, Y.x, Y.y * Y.y), scale);
+}
+
+template <int R, int MODE>
+__global__ void __launch_bounds__(32 * R)
+stft_multi_kernel(const float *__restrict__ x, long long x_stride, long long n_frames, int hop,
+                  float *__restrict__ out, long long out_stride_c, long long out_stride_f,
+                  const float2 *__restrict__ win2, const float2 *__restrict__ tw32,
+                  const float2 *__restrict__ comb, const float2 *__restrict__ post,
+                  long long total_items, int vec_ok) {
+    constexpr int M = 1024 * R, N = 2 * M;
+    extern __shared__ float2 smem[];
+    float2 *s_tw = smem;                       // [32][32] W_1024^(k1 t)
+    float2 *s_tiles = s_tw + FAST_M;           // R padded tiles
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
+    float2 *s_x = s_tiles + warp * FAST_TILE;
+    for (int i = tid; i < FAST_M; i += blockDim.x) s_tw[i] = tw32[i];
+    __syncthreads();
+    const float scale = 1.0f / (4.0f * (float)N * (float)N);
+    for (long long item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const long long c = item / n_frames;
+        const long long f = item - c * n_frames;
+        const float *p = x + c * x_stride + f * hop;
+        float2 v[32];
+#pragma unroll
+        for (int n1 = 0; n1 < 32; n1++) {
+            const int idx = R * (32 * n1 + lane) + warp;      // z[idx] = x[2 idx] + j x[2 idx + 1]
+            float2 xv;
+            if (vec_ok) {
+                xv = __ldg(reinterpret_cast<const float2 *>(p) + idx);
+            } else {
+                xv.x = __ldg(p + 2 * idx);
+                xv.y = __ldg(p + 2 * idx + 1);
+            }
+            v[n1] = __fmul2_rn(xv, __ldg(win2 + idx));
+        }
+        dft32(v);
+#pragma unroll
+        for (int r = 0; r < 32; r++) {
+            const int k1 = brev5(r);
+            const float2 val = (k1 == 0) ? v[r] : cmul(v[r], s_tw[k1 * 32 + lane]);
+            s_x[k1 * 33 + lane] = val;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int n2 = 0; n2 < 32; n2++) v[n2] = s_x[lane * 33 + n2];
+        __syncwarp();
+        dft32(v);   // v[r] = Z_w[lane + 32*brev5(r)]
+#pragma unroll
+        for (int r = 0; r < 32; r++) s_x[lane + 32 * brev5(r)] = v[r];   // natural order
+        __syncthreads();
+
+        float *o = out + c * out_stride_c + f * out_stride_f;
+        for (int k0 = 1 + tid; k0 < 512; k0 += 32 * R) {
+            float2 A[R], B[R];
+            load_group<R>(s_tiles, comb, k0, A);
+            load_group<R>(s_tiles, comb, 1024 - k0, B);
+#pragma unroll
+            for (int q = 0; q < R; q++)
+                split_store<MODE>(o, k0 + 1024 * q, M, A[q], B[R - 1 - q], post, scale);
+        }
+        if (tid == 0) {          // k0 = 0: partners inside the group, q <-> R - q
+            float2 A[R];
+            load_group<R>(s_tiles, comb, 0, A);
+            split_store<MODE>(o, 0, M, A[0], A[0], post, scale);
+#pragma unroll
+            for (int q = 1; q <= R / 2; q++) split_store<MODE>(o, 1024 * q, M, A[q], A[R - q], post, scale);
+        }
+        if (tid == 32) {         // k0 = 512: partners inside the group, q <-> R - 1 - q
+            float2 A[R];
+            load_group<R>(s_tiles, comb, 512, A);
+#pragma unroll
+            for (int q = 0; q < R / 2; q++)
+                split_store<MODE>(o, 512 + 1024 * q, M, A[q], A[R - 1 - q], post, scale);
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Generic path: one CTA per frame, Stockham autosort in shared memory.
 __device__ __forceinline__ void stockham_radix4(const float2 *__restrict__ in,
                                                 float2 *__restrict__ outb,
@@ -482,6 +604,8 @@ void launch_fast(unsigned blocks, cudaStream_t st, const float *x, long long x_s
         pl.tw_dev, pl.post_dev, pl.wlane_dev, total);
 }
 
+size_t multi_smem(int r) { return sizeof(float2) * (FAST_M + (size_t)r * FAST_TILE); }
+
 int ilog2(int v) {
     int l = 0;
     while ((1 << l) < v) l++;
@@ -501,6 +625,7 @@ extern "C" int frt_stft_plan(frt_handle h, int n_fft) {
     if (pl.tw_dev) cudaFree(pl.tw_dev);
     if (pl.post_dev) cudaFree(pl.post_dev);
     if (pl.wlane_dev) cudaFree(pl.wlane_dev);
+    if (pl.comb_dev) cudaFree(pl.comb_dev);
     pl = StftPlan();
     const int N = n_fft, M = N / 2;
     const double PI = 3.14159265358979323846;
@@ -508,8 +633,25 @@ extern "C" int frt_stft_plan(frt_handle h, int n_fft) {
     pl.win_host.resize(N);
     for (int n = 0; n < N; n++)
         pl.win_host[n] = (float)(0.5 * (1.0 - cos(2.0 * PI * n / (double)(N - 1))));
-    std::vector<float2> tw(M), post(M / 2 + 1 + 32);
-    if (N == FAST_N) {
+    const int multi_r = (N == 4096) ? 2 : ((N == 8192) ? 4 : 0);
+    std::vector<float2> tw(M), post(multi_r ? M + 33 : M / 2 + 1 + 32);
+    if (multi_r) {
+        tw.resize(FAST_M);
+        for (int k1 = 0; k1 < 32; k1++)
+            for (int t = 0; t < 32; t++) {
+                const double a = -2.0 * PI * (double)((k1 * t) % FAST_M) / (double)FAST_M;
+                tw[k1 * 32 + t] = make_float2((float)cos(a), (float)sin(a));
+            }
+        std::vector<float2> comb((size_t)(multi_r - 1) * 1024);
+        for (int w = 1; w < multi_r; w++)
+            for (int k0 = 0; k0 < 1024; k0++) {
+                const double a = -2.0 * PI * (double)(w * k0) / (double)M;
+                comb[(size_t)(w - 1) * 1024 + k0] = make_float2((float)cos(a), (float)sin(a));
+            }
+        FRT_CUDA(h, cudaMalloc(&pl.comb_dev, sizeof(float2) * comb.size()));
+        FRT_CUDA(h, cudaMemcpy(pl.comb_dev, comb.data(), sizeof(float2) * comb.size(),
+                               cudaMemcpyHostToDevice));
+    } else if (N == FAST_N) {
         for (int k1 = 0; k1 < 32; k1++)
             for (int t = 0; t < 32; t++) {
                 const double a = -2.0 * PI * (double)((k1 * t) % M) / (double)M;
@@ -547,6 +689,11 @@ extern "C" int frt_stft_plan(frt_handle h, int n_fft) {
                            cudaMemcpyHostToDevice));
     if (N == FAST_N) {
         FRT_CUDA(h, set_fast_smem());
+    } else if (multi_r) {
+        FRT_CUDA(h, cudaFuncSetAttribute(stft_multi_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)multi_smem(2)));
+        FRT_CUDA(h, cudaFuncSetAttribute(stft_multi_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)multi_smem(2)));
+        FRT_CUDA(h, cudaFuncSetAttribute(stft_multi_kernel<4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)multi_smem(4)));
+        FRT_CUDA(h, cudaFuncSetAttribute(stft_multi_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)multi_smem(4)));
     } else {
         FRT_CUDA(h, cudaFuncSetAttribute(stft_generic_kernel,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -602,6 +749,24 @@ extern "C" int frt_stft_process(frt_handle h, const float *x_dev, int64_t x_stri
             else FRT_LAUNCH_FAST(FRT_STFT_LOGPOWER, 0);
         }
 #undef FRT_LAUNCH_FAST
+    } else if (pl.n_fft == 4096 || pl.n_fft == 8192) {
+        const int r = pl.n_fft / 2048;
+        const int vec_ok = (((uintptr_t)x_dev & 7) == 0) && ((x_stride & 1) == 0) && ((hop & 1) == 0);
+        long long blocks = (long long)h->sm_count * (r == 4 ? 4 : 8);
+        if (blocks > total) blocks = total;
+        const float2 *w2 = reinterpret_cast<const float2 *>(pl.win_dev);
+#define FRT_LAUNCH_MULTI(RR, MODE)                                                          \
+    stft_multi_kernel<RR, MODE><<<(unsigned)blocks, 32 * RR, multi_smem(RR), st>>>(          \
+        x_dev, x_stride, n_frames, hop, out_dev, out_stride_c, out_stride_f, w2, pl.tw_dev,  \
+        pl.comb_dev, pl.post_dev, total, vec_ok)
+        if (r == 2) {
+            if (mode == FRT_STFT_POWER) FRT_LAUNCH_MULTI(2, FRT_STFT_POWER);
+            else FRT_LAUNCH_MULTI(2, FRT_STFT_LOGPOWER);
+        } else {
+            if (mode == FRT_STFT_POWER) FRT_LAUNCH_MULTI(4, FRT_STFT_POWER);
+            else FRT_LAUNCH_MULTI(4, FRT_STFT_LOGPOWER);
+        }
+#undef FRT_LAUNCH_MULTI
     } else {
         FRT_CHECK_ARG(h, total <= 0x7fffffffLL, "too many frames for one launch");
         const int M = pl.n_fft / 2;
