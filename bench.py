@@ -377,6 +377,19 @@ def other_workloads(args, dev, rank, world, barrier):
     ms = timed(combined, 3)
     res["combined_stft_plus_27band"] = {"channels_per_gpu": C, "hops_per_channel": nblk - 1, "ms": ms,
                                         "units_per_s": C * (nblk - 1) * world / (ms * 1e-3)}
+    # the widgets' default FFT sizes (spectrogram 4096, spectrum 8192), 75 % overlap as the widgets use
+    for n_fft in (4096, 8192):
+        pw = audioproc(handle=None)
+        pw.set_fftsize(n_fft)
+        hopw = n_fft // 4
+        nfr = (x.shape[1] - n_fft) // hopw + 1
+        outw = torch.empty((256, nfr, n_fft // 2 + 1), dtype=torch.float32, device=dev)
+        ms = timed(lambda: pw.stft(x[:256], hop=hopw, log=True, out=outw), 3)
+        res["stft_%d_overlap75" % n_fft] = {
+            "channels_per_gpu": 256, "frames_per_channel": nfr, "ms": ms,
+            "spectra_per_s": 256 * nfr * world / (ms * 1e-3),
+            "hbm_gbs_algorithmic": 256 * nfr * (hopw + n_fft // 2 + 1) * 4 / (ms * 1e-3) / 1e9}
+        del outw, pw
     # config #4: GCC-PHAT delay estimation, 4096 pairs x L = 24000 (12 kHz-rate signals)
     from friture_b200.correlation import GccPhat
     Pn, Lg = 4096, 24000

@@ -370,7 +370,8 @@ stft2048_kernel(const float *__restrict__ x, long long x_stride, long long n_fra
 }
 
 // ------------------------------------------------------------------------------------------
-// N = 4096 / 8192 (the spectrogram's and the spectrum's default sizes): R = 2 / 4 warps per frame.
+// N = 4096 / 8192 (the spectrogram's and the spectrum's default sizes) and 16384: R = 2 / 4 / 8
+// warps per frame.
 // Warp w runs the 1024-point complex FFT of the decimated sequence z[R n + w] exactly like the
 // N = 2048 kernel (radix-32 x 32 in registers, one transpose through its smem tile), leaves
 // Z_w[k0] in natural order in the tile, and after one block barrier the CTA combines
@@ -390,6 +391,21 @@ template <> __device__ __forceinline__ void combine<4>(float2 (&t)[4]) {
     t[1] = cadd(d02, d13);
     t[2] = csub(s02, s13);
     t[3] = csub(d02, d13);
+}
+
+template <> __device__ __forceinline__ void combine<8>(float2 (&t)[8]) {
+    float2 e[4] = {t[0], t[2], t[4], t[6]}, o[4] = {t[1], t[3], t[5], t[7]};
+    combine<4>(e);
+    combine<4>(o);
+    const float h = 0.70710678118654752440f;
+    // W_8^q o_q: q = 1: (1 - j)/sqrt2, q = 2: -j, q = 3: (-1 - j)/sqrt2
+    const float2 o1 = make_float2(h * (o[1].x + o[1].y), h * (o[1].y - o[1].x));
+    const float2 o2 = mul_mj(o[2]);
+    const float2 o3 = make_float2(h * (o[3].y - o[3].x), -h * (o[3].x + o[3].y));
+    t[0] = cadd(e[0], o[0]); t[4] = csub(e[0], o[0]);
+    t[1] = cadd(e[1], o1);   t[5] = csub(e[1], o1);
+    t[2] = cadd(e[2], o2);   t[6] = csub(e[2], o2);
+    t[3] = cadd(e[3], o3);   t[7] = csub(e[3], o3);
 }
 
 template <int R>
@@ -633,7 +649,7 @@ extern "C" int frt_stft_plan(frt_handle h, int n_fft) {
     pl.win_host.resize(N);
     for (int n = 0; n < N; n++)
         pl.win_host[n] = (float)(0.5 * (1.0 - cos(2.0 * PI * n / (double)(N - 1))));
-    const int multi_r = (N == 4096) ? 2 : ((N == 8192) ? 4 : 0);
+    const int multi_r = (N == 4096) ? 2 : ((N == 8192) ? 4 : ((N == 16384) ? 8 : 0));
     std::vector<float2> tw(M), post(multi_r ? M + 33 : M / 2 + 1 + 32);
     if (multi_r) {
         tw.resize(FAST_M);
@@ -694,6 +710,8 @@ extern "C" int frt_stft_plan(frt_handle h, int n_fft) {
         FRT_CUDA(h, cudaFuncSetAttribute(stft_multi_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)multi_smem(2)));
         FRT_CUDA(h, cudaFuncSetAttribute(stft_multi_kernel<4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)multi_smem(4)));
         FRT_CUDA(h, cudaFuncSetAttribute(stft_multi_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)multi_smem(4)));
+        FRT_CUDA(h, cudaFuncSetAttribute(stft_multi_kernel<8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)multi_smem(8)));
+        FRT_CUDA(h, cudaFuncSetAttribute(stft_multi_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)multi_smem(8)));
     } else {
         FRT_CUDA(h, cudaFuncSetAttribute(stft_generic_kernel,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -749,10 +767,10 @@ extern "C" int frt_stft_process(frt_handle h, const float *x_dev, int64_t x_stri
             else FRT_LAUNCH_FAST(FRT_STFT_LOGPOWER, 0);
         }
 #undef FRT_LAUNCH_FAST
-    } else if (pl.n_fft == 4096 || pl.n_fft == 8192) {
+    } else if (pl.n_fft == 4096 || pl.n_fft == 8192 || pl.n_fft == 16384) {
         const int r = pl.n_fft / 2048;
         const int vec_ok = (((uintptr_t)x_dev & 7) == 0) && ((x_stride & 1) == 0) && ((hop & 1) == 0);
-        long long blocks = (long long)h->sm_count * (r == 4 ? 4 : 8);
+        long long blocks = (long long)h->sm_count * (r == 8 ? 2 : (r == 4 ? 4 : 8));
         if (blocks > total) blocks = total;
         const float2 *w2 = reinterpret_cast<const float2 *>(pl.win_dev);
 #define FRT_LAUNCH_MULTI(RR, MODE)                                                          \
@@ -762,9 +780,12 @@ extern "C" int frt_stft_process(frt_handle h, const float *x_dev, int64_t x_stri
         if (r == 2) {
             if (mode == FRT_STFT_POWER) FRT_LAUNCH_MULTI(2, FRT_STFT_POWER);
             else FRT_LAUNCH_MULTI(2, FRT_STFT_LOGPOWER);
-        } else {
+        } else if (r == 4) {
             if (mode == FRT_STFT_POWER) FRT_LAUNCH_MULTI(4, FRT_STFT_POWER);
             else FRT_LAUNCH_MULTI(4, FRT_STFT_LOGPOWER);
+        } else {
+            if (mode == FRT_STFT_POWER) FRT_LAUNCH_MULTI(8, FRT_STFT_POWER);
+            else FRT_LAUNCH_MULTI(8, FRT_STFT_LOGPOWER);
         }
 #undef FRT_LAUNCH_MULTI
     } else {
