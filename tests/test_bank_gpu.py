@@ -161,6 +161,21 @@ def test_dropin_filter_matches_reference_test_protocol():
         assert np.max(np.abs(acc_g / acc_r - 1.0)) < TOL
 
 
+def test_unaligned_views_take_the_scalar_load_path():
+    """A channel view that is only 4-byte aligned (odd sample offset) gives the same numbers."""
+    import torch
+    from friture_b200.octavefilters import Octave_Filters
+    x = make_x(3, 2048 + 1, seed=12)
+    xd = torch.from_numpy(x).cuda()
+    a = Octave_Filters(3).energies_batch(xd[:, 1:], block=512)                 # misaligned rows
+    b = Octave_Filters(3).energies_batch(xd[:, 1:].contiguous(), block=512)    # aligned copy
+    assert torch.equal(a, b)
+    big = torch.from_numpy(make_x(6200, 513, seed=13)).cuda()                  # one-warp-per-channel kernel
+    a = Octave_Filters(3).energies_batch(big[:, 1:], block=512)
+    b = Octave_Filters(3).energies_batch(big[:, 1:].contiguous(), block=512)
+    assert torch.equal(a, b)
+
+
 def test_bad_arguments():
     import torch
     from friture_b200.octavefilters import Octave_Filters
