@@ -697,7 +697,10 @@ static cudaError_t launch_bank_y(const BankPlan *pl, const BankArgs &a, cudaStre
     // few channels: three warps per channel (latency-bound regime); many channels: one warp
     // per channel already saturates the schedulers with less synchronisation
     static const char *force = getenv("FRT_BANK_WARPS");
-    const bool three = force ? (force[0] == '3') : (a.n_channels < 6144 && L0 <= 16);
+    // the three-warp kernel runs all log2(L0) scan-mode stages unconditionally: it needs more
+    // octaves than that (always true for the 9- and 10-octave banks of the reference)
+    const bool can_three = pl->params.n_oct > Log2<L0>::v;
+    const bool three = can_three && (force ? (force[0] == '3') : (a.n_channels < 6144 && L0 <= 16));
     if (three) return launch_bank3<L0, WANT_Y>(pl, a, st);
     const BankParams &P = pl->params;
     const int warps = 2;
