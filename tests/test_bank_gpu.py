@@ -83,6 +83,19 @@ def test_thirty_bands_ten_octaves():
     assert energy_rel_err(e.cpu().numpy().astype(np.float64), E) < TOL
 
 
+@pytest.mark.parametrize("noct", [1, 3, 5])
+def test_few_octaves(noct):
+    """Banks with fewer octaves than scan-mode stages (API allows 1..10) stay on the one-warp kernel."""
+    import torch
+    from friture_b200.octavefilters import Octave_Filters
+    x = make_x(2, 2048, seed=noct)
+    bank = Octave_Filters(3, n_octaves=noct)
+    e = bank.energies_batch(torch.from_numpy(x).cuda(), block=512)
+    E, _ = oracle_run(bank, x, 512, n_octaves=noct)
+    assert tuple(e.shape) == (2, 4, 3 * noct)
+    assert energy_rel_err(e.cpu().numpy().astype(np.float64), E) < TOL
+
+
 def test_db_output_and_response_times():
     import torch
     from friture_b200.octavefilters import Octave_Filters
