@@ -102,11 +102,14 @@ extern "C" int frt_destroy(frt_handle h) {
     if (!h) return FRT_OK;
     DeviceGuard g(h->device);
     cudaDeviceSynchronize();
-    if (h->stft.win_dev) cudaFree(h->stft.win_dev);
-    if (h->stft.tw_dev) cudaFree(h->stft.tw_dev);
-    if (h->stft.post_dev) cudaFree(h->stft.post_dev);
-    if (h->stft.wlane_dev) cudaFree(h->stft.wlane_dev);
-    if (h->stft.comb_dev) cudaFree(h->stft.comb_dev);
+    for (auto &kv : h->stft_cache) {
+        StftPlan &pl = kv.second;
+        if (pl.win_dev) cudaFree(pl.win_dev);
+        if (pl.tw_dev) cudaFree(pl.tw_dev);
+        if (pl.post_dev) cudaFree(pl.post_dev);
+        if (pl.wlane_dev) cudaFree(pl.wlane_dev);
+        if (pl.comb_dev) cudaFree(pl.comb_dev);
+    }
     frt_bank_release(h);
     frt_gcc_release(h);
     frt_dec_release(h);

@@ -5,6 +5,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -37,7 +38,8 @@ struct frt_ctx {
     int sm_count = 0;
     int64_t launches = 0;
     std::string err;
-    StftPlan stft;
+    StftPlan stft;                       // current plan (a copy of one cache entry)
+    std::map<int, StftPlan> stft_cache;  // every size planned so far owns its device tables
     HostPipe pipe;
     BankPlan *bank = nullptr;
     GccPlan *gcc = nullptr;

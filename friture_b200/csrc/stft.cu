@@ -635,14 +635,14 @@ extern "C" int frt_stft_plan(frt_handle h, int n_fft) {
     DeviceGuard g(h->device);
     FRT_CHECK_ARG(h, n_fft >= 32 && n_fft <= 16384 && (n_fft & (n_fft - 1)) == 0,
                   "n_fft must be a power of two in [32, 16384]");
-    StftPlan &pl = h->stft;
-    if (pl.n_fft == n_fft) return FRT_OK;
-    if (pl.win_dev) cudaFree(pl.win_dev);
-    if (pl.tw_dev) cudaFree(pl.tw_dev);
-    if (pl.post_dev) cudaFree(pl.post_dev);
-    if (pl.wlane_dev) cudaFree(pl.wlane_dev);
-    if (pl.comb_dev) cudaFree(pl.comb_dev);
-    pl = StftPlan();
+    if (h->stft.n_fft == n_fft) return FRT_OK;
+    // plans are cached per size: the spectrum (8192) and spectrogram (4096) widgets share a handle
+    auto cached = h->stft_cache.find(n_fft);
+    if (cached != h->stft_cache.end()) {
+        h->stft = cached->second;
+        return FRT_OK;
+    }
+    StftPlan pl;
     const int N = n_fft, M = N / 2;
     const double PI = 3.14159265358979323846;
     // symmetric Hann, friture/audioproc.py:76-81
@@ -718,6 +718,8 @@ extern "C" int frt_stft_plan(frt_handle h, int n_fft) {
                                          (int)(sizeof(float2) * 2 * 8192)));
     }
     pl.n_fft = n_fft;
+    h->stft_cache[n_fft] = pl;
+    h->stft = pl;
     return FRT_OK;
 }
 

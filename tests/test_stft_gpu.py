@@ -139,3 +139,22 @@ def test_unaligned_input_uses_scalar_loads():
     got = proc.stft(xd, hop=1024).cpu().numpy().astype(np.float64)
     ref = fo.log_spectrogram(fo.stft_power_batch(x[:, 1:], 2048, 1024))
     assert_logpower_parity(got, ref)
+
+
+def test_plan_cache_alternating_sizes():
+    """Two processors of different FFT sizes sharing one handle (as the spectrum and spectrogram
+    widgets would) can be called alternately; the handle keeps one plan per size."""
+    import torch
+    from friture_b200 import audioproc
+    from oracle import friture_oracle as fo
+    x = make_input("randn", 2, 8192 + 3 * 2048, seed=21)
+    xd = torch.from_numpy(x).cuda()
+    pa, pb = audioproc(), audioproc()
+    pa.set_fftsize(8192)
+    pb.set_fftsize(4096)
+    assert pa.handle is pb.handle
+    for _ in range(3):
+        a = pa.stft(xd, hop=2048).cpu().numpy().astype(np.float64)
+        b = pb.stft(xd, hop=1024).cpu().numpy().astype(np.float64)
+    assert_logpower_parity(a, fo.log_spectrogram(fo.stft_power_batch(x, 8192, 2048)))
+    assert_logpower_parity(b, fo.log_spectrogram(fo.stft_power_batch(x, 4096, 1024)))
