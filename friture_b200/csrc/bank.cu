@@ -695,12 +695,14 @@ static cudaError_t launch_bank3(const BankPlan *pl, const BankArgs &a, cudaStrea
 template <int L0, bool WANT_Y>
 static cudaError_t launch_bank_y(const BankPlan *pl, const BankArgs &a, cudaStream_t st) {
     // few channels: three warps per channel (latency-bound regime); many channels: one warp
-    // per channel already saturates the schedulers with less synchronisation
+    // per channel already saturates the schedulers with less synchronisation.  Measured on B200
+    // (blocks/s, 512-sample blocks, one / three warps): 1024 ch 4.1e7 / 5.3e7, 2048 ch 5.6e7 / 5.0e7,
+    // 4096 ch 6.7e7 / 5.2e7, 8192 ch 6.8e7 / 5.5e7
     static const char *force = getenv("FRT_BANK_WARPS");
     // the three-warp kernel runs all log2(L0) scan-mode stages unconditionally: it needs more
     // octaves than that (always true for the 9- and 10-octave banks of the reference)
     const bool can_three = pl->params.n_oct > Log2<L0>::v;
-    const bool three = can_three && (force ? (force[0] == '3') : (a.n_channels < 6144 && L0 <= 16));
+    const bool three = can_three && (force ? (force[0] == '3') : (a.n_channels < 1536 && L0 <= 16));
     if (three) return launch_bank3<L0, WANT_Y>(pl, a, st);
     const BankParams &P = pl->params;
     const int warps = 2;
