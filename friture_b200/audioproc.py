@@ -18,6 +18,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import STFT_LOGPOWER, STFT_POWER, default_handle
+from .weighting import abc_weighting
 
 SAMPLING_RATE = 48000      # friture/audiobackend.py:31
 FRAMES_PER_BUFFER = 512    # friture/audiobackend.py:32
@@ -73,16 +74,12 @@ class audioproc():
     def set_fftsize(self, fft_size):
         if fft_size != self.fft_size:
             self.fft_size = fft_size
-            self.update_freq_cache()
-            self.update_window()
-            self.update_size()
+            self._refresh()
 
     def set_maxfreq(self, maxfreq):
         if maxfreq != self.maxfreq:
             self.maxfreq = maxfreq
-            self.update_freq_cache()
-            self.update_window()
-            self.update_size()
+            self._refresh()
 
     def get_freq_scale(self):
         return self.freq
@@ -90,30 +87,29 @@ class audioproc():
     def get_freq_weighting(self):
         return self.A, self.B, self.C
 
+    def _refresh(self):
+        # the three updates the reference runs on every size / range change (audioproc.py:52-66)
+        self.update_freq_cache()
+        self.update_window()
+        self.update_size()
+
     def update_size(self):
         self.size_sq = float(self.fft_size) ** 2
 
     def update_window(self):
-        # the device plan builds the same symmetric Hann (friture/audioproc.py:76-81) in float64
-        # and rounds it to float32; ``window`` exposes the float64 form like the reference
-        N = self.fft_size
-        n = np.arange(0, N)
-        self.window = 0.5 * (1. - np.cos(2 * np.pi * n / (N - 1)))
+        # symmetric Hann 0.5*(1 - cos(2*pi*n/(N-1))), friture/audioproc.py:76-81; the device plan
+        # builds the same window in float64 and rounds it to float32, `window` exposes float64
+        n = np.arange(self.fft_size)
+        self.window = 0.5 * (1. - np.cos(2 * np.pi * n / (self.fft_size - 1)))
         self.logger.info("audioproc: updating window")
 
     def update_freq_cache(self):
-        # friture/audioproc.py:83-96
-        if len(self.freq) != self.fft_size / 2 + 1:
+        # bin frequencies and A/B/C weighting tables, friture/audioproc.py:83-96
+        nbins = self.fft_size // 2 + 1
+        if len(self.freq) != nbins:
             self.logger.info("audioproc: updating self.freq cache")
-            self.freq = np.linspace(0, SAMPLING_RATE // 2, self.fft_size // 2 + 1)
-            f = self.freq
-            Rc = 12200. ** 2 * f ** 2 / ((f ** 2 + 20.6 ** 2) * (f ** 2 + 12200. ** 2))
-            Rb = 12200. ** 2 * f ** 3 / ((f ** 2 + 20.6 ** 2) * (f ** 2 + 12200. ** 2) * ((f ** 2 + 158.5 ** 2) ** 0.5))
-            Ra = 12200. ** 2 * f ** 4 / ((f ** 2 + 20.6 ** 2) * (f ** 2 + 12200. ** 2) * ((f ** 2 + 107.7 ** 2) ** 0.5) * ((f ** 2 + 737.9 ** 2) ** 0.5))
-            eps = 1e-50
-            self.C = 0.06 + 20. * np.log10(Rc + eps)
-            self.B = 0.17 + 20. * np.log10(Rb + eps)
-            self.A = 2.0 + 20. * np.log10(Ra + eps)
+            self.freq = np.linspace(0, SAMPLING_RATE // 2, nbins)
+            self.A, self.B, self.C = abc_weighting(self.freq, eps=1e-50)
 
     # ------------------------------------------------------------------ batched extensions
     def stft(self, x, hop, log=True, out=None, stream=None):

@@ -23,6 +23,7 @@ from . import _lib, filter_data
 from ._lib import Handle
 from .audioproc import SAMPLING_RATE
 from .filter_data import NOCTAVE
+from .weighting import abc_weighting
 
 FIR_LENGTH = 512   # friture/octavefilters.py:35 (kept for attribute parity; unused by the IIR kernel)
 MAX_BLOCK = 8192   # exp_smoothed_value drops history beyond its 8192/dec-tap kernel
@@ -110,13 +111,7 @@ class Octave_Filters():
         self.boct = [np.array(f) for f in boct]
         self.aoct = [np.array(f) for f in aoct]
         self._sos_band = np.ascontiguousarray(sos, dtype=np.float64)
-        f = self.fi
-        Rc = 12200. ** 2 * f ** 2 / ((f ** 2 + 20.6 ** 2) * (f ** 2 + 12200. ** 2))
-        Rb = 12200. ** 2 * f ** 3 / ((f ** 2 + 20.6 ** 2) * (f ** 2 + 12200. ** 2) * ((f ** 2 + 158.5 ** 2) ** 0.5))
-        Ra = 12200. ** 2 * f ** 4 / ((f ** 2 + 20.6 ** 2) * (f ** 2 + 12200. ** 2) * ((f ** 2 + 107.7 ** 2) ** 0.5) * ((f ** 2 + 737.9 ** 2) ** 0.5))
-        self.C = 0.06 + 20. * np.log10(Rc)
-        self.B = 0.17 + 20. * np.log10(Rb)
-        self.A = 2.0 + 20. * np.log10(Ra)
+        self.A, self.B, self.C = abc_weighting(self.fi)     # friture/octavefilters.py:76-82
         self._plan_key = None   # new filters -> state restarts from zero (octavefilters.py:151-158)
         self.f_nominal = self._nominal_labels()
 
