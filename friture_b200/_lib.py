@@ -56,6 +56,8 @@ SIGNATURES = {
                                       c_void_p, c_int]),
     "frt_bank_plan": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "frt_bank_reset": (c_int, [c_void_p]),
+    "frt_bank_set_weighting": (c_int, [c_void_p, c_void_p]),
+    "frt_bank_schedule": (c_int, [c_int, c_int, c_int64, c_void_p, c_void_p]),
     "frt_bank_process": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p,
                                  c_int64, c_int, c_void_p]),
     "frt_bank_state_size": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64)]),

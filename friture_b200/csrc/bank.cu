@@ -22,38 +22,13 @@
 #include <cmath>
 #include <cstdlib>
 
-#include "frt_internal.cuh"
+#include "bank_internal.cuh"
 
 namespace {
 
-constexpr int MAX_BPO = 24;
-constexpr int MAX_SEC = 2 * MAX_BPO + 6;
-constexpr int MAX_OCT = 10;
-constexpr int NQ = 10;   // A^(2^q), q = 0..9: chunk L <= 32 (q <= 5) plus 4 doublings
-
-struct BankParams {
-    float coef[MAX_SEC][8];        // b0 b1 b2 a1 a2 B1 B2 -, B = (b1 - a1 b0, b2 - a2 b0)
-    float apow[MAX_SEC][NQ][4];    // A^(2^q), A = [[-a1, 1], [-a2, 0]], row-major
-    float qpow[MAX_OCT][NQ];       // (1 - alpha_j)^(2^q)
-    float alpha[MAX_OCT];
-    int bpo, n_oct, nsec;          // nsec = 2*bpo + 6; band i section s -> 2*i+s; dec s -> 2*bpo+s
-};
-
-struct BankArgs {
-    const float *x;
-    long long x_stride;
-    int n_channels;
-    int n_tiles;           // tiles per launch (per channel)
-    int tiles_per_block;   // energies are emitted after every tiles_per_block-th tile
-    float *zstate;         // [C][n_oct][nsec][2]
-    float *ema;            // [C][n_oct][bpo]   smoothed energies / alpha_j (dispbuffers / alpha)
-    float *energies;       // [C][n_blocks][nbands] or NULL
-    float *y;              // ragged band outputs or NULL
-    long long y_stride;
-    long long t_total;     // samples per channel in this launch (n_tiles * tile)
-    int db;                // 1: energies as 10*log10(e + 1e-30)
-    int vec_ok;
-};
+constexpr int MAX_BPO = BANK_MAX_BPO;
+constexpr int MAX_OCT = BANK_MAX_OCT;
+constexpr int NQ = BANK_NQ;
 
 __device__ __forceinline__ float lg2_fast(float v) {
     float r;
@@ -61,9 +36,12 @@ __device__ __forceinline__ float lg2_fast(float v) {
     return r;
 }
 
-__device__ __forceinline__ float energy_out(float e, int db) {
-    // friture/octavespectrum.py:119-120: 10*log10(sp + 1e-30)
-    return db ? 3.01029995663981195f * lg2_fast(e + 1e-30f) : e;
+__device__ __forceinline__ float energy_out(float e, int db, const float *weight, int kband) {
+    // friture/octavespectrum.py:119-121: 10*log10(sp + 1e-30) + w
+    if (!db) return e;
+    float v = 3.01029995663981195f * lg2_fast(e + 1e-30f);
+    if (weight) v += __ldg(weight + kband);
+    return v;
 }
 
 // offset of band k in the ragged per-channel y layout (bands concatenated, k = 0 lowest)
@@ -90,6 +68,7 @@ struct WarpCtxT {
     long long t_off;  // sample offset of this tile within the launch
     int lane;
     int db;
+    const float *weight;   // dB offsets per band (db mode) or NULL
 };
 
 // ---------------------------------------------------------------- scan-mode section
@@ -165,29 +144,33 @@ __device__ __forceinline__ void bands_of_stage(const float (&xc)[L], const W &w,
         section_scan<L>(xc, wk, w, j, 2 * i);
         section_scan<L>(wk, wk, w, j, 2 * i + 1);
         const int kband = (P.n_oct - 1 - j) * bpo + i;
+        const float gb = P.gband[i];     // chain gain of the normalised sections
+#pragma unroll
+        for (int k = 0; k < L; k++) wk[k] *= gb;
         if constexpr (W::kWantY) {
             float *yp = w.y + y_offset(kband, bpo, P.n_oct, w.t_total) + (w.t_off >> j) +
                         w.lane * L;
 #pragma unroll
             for (int k = 0; k < L; k++) yp[k] = wk[k];
         }
-        // exponential smoothing of y^2 (friture/signal/exp_smoothing.py:11-56), e/alpha form
-        const float q = P.qpow[j][0];
+        // exponential smoothing of y^2 (friture/signal/exp_smoothing.py:11-56), e/alpha form;
+        // decays in complement form e - (1-q^n) e: the rounding of q must not bias long time constants
+        const float om = P.omq[j][0];
         float e = 0.f;
 #pragma unroll
-        for (int k = 0; k < L; k++) e = fmaf(e, q, wk[k] * wk[k]);
+        for (int k = 0; k < L; k++) e = fmaf(-om, e, e) + wk[k] * wk[k];
         float *ep = w.s_e + j * bpo + i;
         constexpr int q0 = Log2<L>::v;
-        if (w.lane == 0) e = fmaf(P.qpow[j][q0], ep[0], e);
+        if (w.lane == 0) e += fmaf(-P.omq[j][q0], ep[0], ep[0]);
 #pragma unroll
         for (int k = 0; k < 5; k++) {
             const float t = __shfl_up_sync(0xffffffffu, e, 1 << k);
-            if (w.lane >= (1 << k)) e = fmaf(P.qpow[j][q0 + k], t, e);
+            if (w.lane >= (1 << k)) e += fmaf(-P.omq[j][q0 + k], t, t);
         }
         __syncwarp();
         if (w.lane == 31) {
             ep[0] = e;
-            if (w.energies) w.energies[kband] = energy_out(P.alpha[j] * e, w.db);
+            if (w.energies) w.energies[kband] = energy_out(P.alpha[j] * e, w.db, w.weight, kband);
         }
     }
 }
@@ -214,11 +197,11 @@ __device__ void scan_stage(const float (&xc)[L], const W &w, int j) {
     if constexpr (L >= 4) {
         float xn[L / 2];
 #pragma unroll
-        for (int k = 0; k < L / 2; k++) xn[k] = wk[2 * k];
+        for (int k = 0; k < L / 2; k++) xn[k] = wk[2 * k] * P.gdec;
         scan_stage<L / 2>(xn, w, j + 1);
     } else {
         // L == 2: one sample per lane is left -> switch to lane = chain
-        serial_stages<W>(wk[0], 32, w, j + 1);
+        serial_stages<W>(wk[0] * P.gdec, 32, w, j + 1);
     }
 }
 
@@ -239,13 +222,13 @@ __device__ void stage_D(const float (&xc)[L], const W &w, int j, float *s_x, flo
         float *dst = s_x + w.lane * (L / 2);     // stage j+1 chunk of this lane
 #pragma unroll
         for (int k = 0; k < L / 2; k++) {
-            xn[k] = wk[2 * k];
+            xn[k] = wk[2 * k] * w.P->gdec;
             dst[k] = xn[k];
         }
         bar_db();
         stage_D<L / 2>(xn, w, j + 1, s_x + 32 * (L / 2), s_x32);
     } else {
-        s_x32[w.lane] = wk[0];                   // 32 samples for the serial stages (warp S)
+        s_x32[w.lane] = wk[0] * w.P->gdec;       // 32 samples for the serial stages (warp S)
         bar_db();
     }
 }
@@ -288,7 +271,8 @@ __device__ __forceinline__ void serial_stages(float xin, int n, const W &w, int 
             z1[s] = zp[0];
             z2[s] = zp[1];
         }
-        const float q = P.qpow[j][0];
+        const float om = P.omq[j][0];
+        const float gout = is_band ? P.gband[is_band ? lane : 0] : P.gdec;   // chain gain
         float e = is_band ? w.s_e[j * bpo + lane] : 0.f;
         const int kband = (P.n_oct - 1 - j) * bpo + (is_band ? lane : 0);
         float *yp = nullptr;
@@ -308,8 +292,9 @@ __device__ __forceinline__ void serial_stages(float xin, int n, const W &w, int 
                     v = y;
                 }
             }
+            v *= gout;
             if (is_band) {
-                e = fmaf(e, q, v * v);
+                e = fmaf(-om, e, e) + v * v;
                 if constexpr (W::kWantY) {
                     if (yp) yp[m] = v;
                 }
@@ -330,7 +315,7 @@ __device__ __forceinline__ void serial_stages(float xin, int n, const W &w, int 
         }
         if (is_band) {
             w.s_e[j * bpo + lane] = e;
-            if (w.energies) w.energies[kband] = energy_out(P.alpha[j] * e, w.db);
+            if (w.energies) w.energies[kband] = energy_out(P.alpha[j] * e, w.db, w.weight, kband);
         }
         __syncwarp();
         xin = xnext;
@@ -369,6 +354,7 @@ bank_kernel(const __grid_constant__ BankParams P, const BankArgs a) {
     w.s_coef = s_coef;
     w.lane = lane;
     w.db = a.db;
+    w.weight = a.weight;
     w.t_total = a.t_total;
     w.y = a.y ? a.y + (size_t)c * a.y_stride : nullptr;
     const float *xch = a.x + (size_t)c * a.x_stride;
@@ -430,6 +416,7 @@ bank_kernel3(const __grid_constant__ BankParams P, const BankArgs a) {
     w.s_coef = s_coef;
     w.lane = lane;
     w.db = a.db;
+    w.weight = a.weight;
     w.t_total = a.t_total;
     w.y = a.y ? a.y + (size_t)c * a.y_stride : nullptr;
     const float *xch = a.x + (size_t)c * a.x_stride;
@@ -492,13 +479,13 @@ __device__ void dec_chain(const float (&xc)[L], const W &w, int j, int n_stages,
     dec_of_stage<L>(xc, wk, w, j);
     if (j + 1 == n_stages) {
 #pragma unroll
-        for (int k = 0; k < L / 2; k++) dst[w.lane * (L / 2) + k] = wk[2 * k];
+        for (int k = 0; k < L / 2; k++) dst[w.lane * (L / 2) + k] = wk[2 * k] * w.P->gdec;
         return;
     }
     if constexpr (L >= 4) {
         float xn[L / 2];
 #pragma unroll
-        for (int k = 0; k < L / 2; k++) xn[k] = wk[2 * k];
+        for (int k = 0; k < L / 2; k++) xn[k] = wk[2 * k] * w.P->gdec;
         dec_chain<L / 2>(xn, w, j + 1, n_stages, dst);
     }
 }
@@ -524,6 +511,7 @@ decimate_kernel(const __grid_constant__ BankParams P, const DecArgs a) {
     w.y = nullptr;
     w.lane = lane;
     w.db = 0;
+    w.weight = nullptr;
     w.t_total = 0;
     w.t_off = 0;
     const int out_tile = TILE >> a.n_stages;
@@ -540,18 +528,11 @@ decimate_kernel(const __grid_constant__ BankParams P, const DecArgs a) {
 
 }   // namespace
 
-struct BankPlan {
-    BankParams params;
-    int n_channels = 0;
-    float *zstate = nullptr;
-    float *ema = nullptr;
-    size_t nz = 0, ne = 0;   // floats per channel
-};
-
 void frt_bank_release(frt_ctx *h) {
     if (!h->bank) return;
     if (h->bank->zstate) cudaFree(h->bank->zstate);
     if (h->bank->ema) cudaFree(h->bank->ema);
+    if (h->bank->weight) cudaFree(h->bank->weight);
     delete h->bank;
     h->bank = nullptr;
 }
@@ -581,6 +562,8 @@ extern "C" int frt_bank_plan(frt_handle h, int n_channels, int bands_per_octave,
     P.bpo = bands_per_octave;
     P.n_oct = n_octaves;
     P.nsec = 2 * bands_per_octave + 6;
+    double gchain[BANK_MAX_BPO + 1];
+    for (int i = 0; i <= bands_per_octave; i++) gchain[i] = 1.0;
     for (int sec = 0; sec < P.nsec; sec++) {
         const double *s = sec < 2 * bands_per_octave ? sos_band + (size_t)sec * 6
                                                      : sos_dec + (size_t)(sec - 2 * bands_per_octave) * 6;
@@ -588,14 +571,19 @@ extern "C" int frt_bank_plan(frt_handle h, int n_channels, int bands_per_octave,
             delete pl;
             return frt_fail(h, FRT_EINVAL, "SOS section %d has a0 != 1", sec);
         }
-        const double b0 = s[0], b1 = s[1], b2 = s[2], a1 = s[4], a2 = s[5];
-        P.coef[sec][0] = (float)b0; P.coef[sec][1] = (float)b1; P.coef[sec][2] = (float)b2;
+        // elliptic sections have their zeros on the unit circle: b = g (1, c, 1)
+        if (!(fabs(s[0]) > 0.0) || fabs(s[2] / s[0] - 1.0) > 1e-7) {
+            delete pl;
+            return frt_fail(h, FRT_EINVAL, "SOS section %d: b2 != b0 (zeros off the unit circle)", sec);
+        }
+        gchain[sec < 2 * bands_per_octave ? sec / 2 : bands_per_octave] *= s[0];
+        const double cmid = s[1] / s[0], a1 = s[4], a2 = s[5];
+        P.coef[sec][0] = 1.f; P.coef[sec][1] = (float)cmid; P.coef[sec][2] = 1.f;
         P.coef[sec][3] = (float)a1; P.coef[sec][4] = (float)a2;
         // the scan must propagate the state of the float32 filter that pass 2 runs
-        const double fb0 = P.coef[sec][0], fb1 = P.coef[sec][1], fb2 = P.coef[sec][2];
-        const double fa1 = P.coef[sec][3], fa2 = P.coef[sec][4];
-        P.coef[sec][5] = (float)(fb1 - fa1 * fb0);
-        P.coef[sec][6] = (float)(fb2 - fa2 * fb0);
+        const double fb1 = P.coef[sec][1], fa1 = P.coef[sec][3], fa2 = P.coef[sec][4];
+        P.coef[sec][5] = (float)(fb1 - fa1);
+        P.coef[sec][6] = (float)(1.0 - fa2);
         double A[4] = {-fa1, 1.0, -fa2, 0.0};
         for (int q = 0; q < NQ; q++) {
             for (int i = 0; i < 4; i++) P.apow[sec][q][i] = (float)A[i];
@@ -604,18 +592,22 @@ extern "C" int frt_bank_plan(frt_handle h, int n_channels, int bands_per_octave,
             memcpy(A, A2, sizeof(A));
         }
     }
+    for (int i = 0; i < bands_per_octave; i++) P.gband[i] = (float)gchain[i];
+    P.gdec = (float)gchain[bands_per_octave];
     for (int j = 0; j < n_octaves; j++) {
         if (!(alphas[j] > 0.0 && alphas[j] <= 1.0)) {
             delete pl;
             return frt_fail(h, FRT_EINVAL, "alpha[%d] must be in (0, 1]", j);
         }
         P.alpha[j] = (float)alphas[j];
+        pl->alphas[j] = alphas[j];
         double q = 1.0 - alphas[j];
         for (int k = 0; k < NQ; k++) {
-            P.qpow[j][k] = (float)q;
+            P.omq[j][k] = (float)(1.0 - q);
             q *= q;
         }
     }
+    frt_pipe_prepare(pl);
     pl->n_channels = n_channels;
     pl->nz = (size_t)n_octaves * P.nsec * 2;
     pl->ne = (size_t)n_octaves * bands_per_octave;
@@ -640,6 +632,34 @@ extern "C" int frt_bank_reset(frt_handle h) {
     BankPlan *pl = h->bank;
     FRT_CUDA(h, cudaMemset(pl->zstate, 0, sizeof(float) * pl->nz * pl->n_channels));
     FRT_CUDA(h, cudaMemset(pl->ema, 0, sizeof(float) * pl->ne * pl->n_channels));
+    return FRT_OK;
+}
+
+extern "C" int frt_bank_set_weighting(frt_handle h, const float *weight_db_host) {
+    if (!h) return FRT_EINVAL;
+    if (!h->bank) return frt_fail(h, FRT_ESTATE, "frt_bank_set_weighting: no plan");
+    DeviceGuard g(h->device);
+    BankPlan *pl = h->bank;
+    const size_t nb = (size_t)pl->params.n_oct * pl->params.bpo;
+    FRT_CUDA(h, cudaDeviceSynchronize());
+    if (!weight_db_host) {
+        if (pl->weight) cudaFree(pl->weight);
+        pl->weight = nullptr;
+        return FRT_OK;
+    }
+    if (!pl->weight) FRT_CUDA(h, cudaMalloc(&pl->weight, sizeof(float) * nb));
+    FRT_CUDA(h, cudaMemcpy(pl->weight, weight_db_host, sizeof(float) * nb, cudaMemcpyHostToDevice));
+    return FRT_OK;
+}
+
+extern "C" int frt_bank_schedule(int n_octaves, int log2_chunk, int64_t n_samples, int *stage_start,
+                                 int *n_steps) {
+    if (n_octaves < 1 || n_octaves > MAX_OCT || (log2_chunk != 5 && log2_chunk != 6) || !stage_start ||
+        n_samples < 0)
+        return FRT_EINVAL;
+    int T[BANK_MAX_OCT + 1];
+    frt_pipe_schedule(n_octaves, log2_chunk, n_samples, T, n_steps);
+    for (int j = 0; j < MAX_OCT; j++) stage_start[j] = T[j];
     return FRT_OK;
 }
 
@@ -757,9 +777,31 @@ extern "C" int frt_bank_process(frt_handle h, const float *x_dev, int64_t x_stri
     a.t_total = t_total;
     a.db = db;
     a.vec_ok = (((uintptr_t)x_dev & 15) == 0) && ((x_stride & 3) == 0);
+    a.weight = db ? pl->weight : nullptr;
+    a.block = block;
+    a.n_blocks = n_blocks;
+    a.n_steps = 0;
     cudaError_t e;
     cudaStream_t st = (cudaStream_t)stream;
-    if (tile == 1024) e = launch_bank<32>(pl, a, st);
+    // Kernel choice.  The lane-pipelined kernel (bank_pipe.cu) computes every section sample once
+    // and is the fast path for the fused energies of 1- and 1/3-octave banks; the chunk-scan
+    // kernels below serve the ragged band outputs (`.filter()`), 6/12/24 bands per octave and
+    // block lengths that are not a power of two.  FRT_BANK_KERNEL=scan|pipe, FRT_BANK_PACK=1|2 and
+    // FRT_BANK_LOGCH=5|6 override the choice (tuning knobs).
+    const char *force_k = getenv("FRT_BANK_KERNEL");
+    const char *force_p = getenv("FRT_BANK_PACK");
+    const char *force_c = getenv("FRT_BANK_LOGCH");
+    const bool pow2 = (block & (block - 1)) == 0;
+    bool use_pipe = pl->pipe_ok && !y_dev && pow2 && (block >> (P.n_oct - 1)) >= 1;
+    if (force_k && force_k[0] == 's') use_pipe = false;
+    if (use_pipe) {
+        int pack = pl->n_channels >= 2048 ? 2 : 1;
+        int logch = (block >= 512 && n_blocks >= 8) ? 6 : 5;
+        if (force_p) pack = force_p[0] == '2' ? 2 : 1;
+        if (force_c) logch = force_c[0] == '6' ? 6 : 5;
+        if (block < (1 << logch) * 4) logch = 5;
+        e = frt_pipe_launch(pl, a, logch, pack, st);
+    } else if (tile == 1024) e = launch_bank<32>(pl, a, st);
     else if (tile == 512) e = launch_bank<16>(pl, a, st);
     else e = launch_bank<8>(pl, a, st);
     h->launches++;
@@ -797,14 +839,19 @@ extern "C" int frt_decimate_plan(frt_handle h, int n_channels, int n_stages, con
     P.bpo = 0;          // section index 2*bpo + s = s: the six decimator sections
     P.n_oct = n_stages;
     P.nsec = 6;
+    double gdec = 1.0;
     for (int sec = 0; sec < 6; sec++) {
         const double *s = sos_dec + (size_t)sec * 6;
-        P.coef[sec][0] = (float)s[0]; P.coef[sec][1] = (float)s[1]; P.coef[sec][2] = (float)s[2];
+        if (!(fabs(s[0]) > 0.0) || fabs(s[2] / s[0] - 1.0) > 1e-7 || fabs(s[3] - 1.0) > 1e-12) {
+            delete pl;
+            return frt_fail(h, FRT_EINVAL, "decimator section %d is not of the form g(1,c,1)/(1,a1,a2)", sec);
+        }
+        gdec *= s[0];
+        P.coef[sec][0] = 1.f; P.coef[sec][1] = (float)(s[1] / s[0]); P.coef[sec][2] = 1.f;
         P.coef[sec][3] = (float)s[4]; P.coef[sec][4] = (float)s[5];
-        const double fb0 = P.coef[sec][0], fb1 = P.coef[sec][1], fb2 = P.coef[sec][2];
-        const double fa1 = P.coef[sec][3], fa2 = P.coef[sec][4];
-        P.coef[sec][5] = (float)(fb1 - fa1 * fb0);
-        P.coef[sec][6] = (float)(fb2 - fa2 * fb0);
+        const double fb1 = P.coef[sec][1], fa1 = P.coef[sec][3], fa2 = P.coef[sec][4];
+        P.coef[sec][5] = (float)(fb1 - fa1);
+        P.coef[sec][6] = (float)(1.0 - fa2);
         double A[4] = {-fa1, 1.0, -fa2, 0.0};
         for (int q = 0; q < NQ; q++) {
             for (int i = 0; i < 4; i++) P.apow[sec][q][i] = (float)A[i];
@@ -813,6 +860,7 @@ extern "C" int frt_decimate_plan(frt_handle h, int n_channels, int n_stages, con
             memcpy(A, A2, sizeof(A));
         }
     }
+    P.gdec = (float)gdec;
     pl->n_channels = n_channels;
     pl->n_stages = n_stages;
     const size_t nz = (size_t)n_stages * 6 * 2 * n_channels;

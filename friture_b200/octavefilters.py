@@ -76,6 +76,7 @@ class Octave_Filters():
         self._n_octaves = n_octaves
         self._response_time = response_time
         self._plan_key = None
+        self._weighting = None
         self.setbandsperoctave(bandsperoctave)
 
     # ------------------------------------------------------------------ reference surface
@@ -112,6 +113,7 @@ class Octave_Filters():
         self.aoct = [np.array(f) for f in aoct]
         self._sos_band = np.ascontiguousarray(sos, dtype=np.float64)
         self.A, self.B, self.C = abc_weighting(self.fi)     # friture/octavefilters.py:76-82
+        self._weighting = None
         self._plan_key = None   # new filters -> state restarts from zero (octavefilters.py:151-158)
         self.f_nominal = self._nominal_labels()
 
@@ -168,6 +170,23 @@ class Octave_Filters():
         if self._plan_key is not None:
             self.handle.call("frt_bank_reset")
 
+    def set_weighting(self, weighting):
+        """dB offsets added to the dB energies (``db=True``), as the octave widget does
+        (friture/octavespectrum.py:108-121): None / 0 = none, 'A' / 'B' / 'C' or 1 / 2 / 3 = the
+        reference's tables (friture/octavefilters.py:76-82), or an array of nbands values."""
+        if weighting is None or (isinstance(weighting, (int, np.integer)) and weighting == 0):
+            w = None
+        elif isinstance(weighting, str) or isinstance(weighting, (int, np.integer)):
+            key = {"A": "A", "B": "B", "C": "C", 1: "A", 2: "B", 3: "C"}[weighting]
+            w = np.asarray(getattr(self, key), dtype=np.float32)
+        else:
+            w = np.ascontiguousarray(weighting, dtype=np.float32)
+            if w.shape != (self.nbands,):
+                raise ValueError("weighting must have nbands = %d values" % self.nbands)
+        self._weighting = w
+        if self._plan_key is not None:
+            self.handle.call("frt_bank_set_weighting", _lib._ptr(self._weighting))
+
     def _ensure_plan(self, n_channels):
         key = (n_channels, self.bandsperoctave, self._n_octaves, self._response_time)
         if key == self._plan_key:
@@ -179,6 +198,8 @@ class Octave_Filters():
                          _lib._ptr(alphas))
         self._plan_key = key
         self.alphas = alphas
+        if self._weighting is not None:
+            self.handle.call("frt_bank_set_weighting", _lib._ptr(self._weighting))
 
     # ------------------------------------------------------------------ batched extensions
     def filter_batch(self, x, block, energies=True, want_y=False, db=False, stream=None):

@@ -92,6 +92,17 @@ int frt_stft_process_host(frt_handle h, const float *x_host, int64_t x_stride, i
 int frt_bank_plan(frt_handle h, int n_channels, int bands_per_octave, int n_octaves,
                   const double *sos_band, const double *sos_dec, const double *alphas);
 int frt_bank_reset(frt_handle h);
+/* Per-band dB offsets added to the energies when db != 0 -- the octave widget's weighting,
+ * `10*log10(sp+1e-30) + w` with w = Octave_Filters.A / .B / .C (friture/octavespectrum.py:108-121,
+ * friture/octavefilters.py:76-82).  weight_db_host: nbands floats (band k as below), or NULL for
+ * no weighting.  Belongs to the current plan (a new frt_bank_plan clears it).                   */
+int frt_bank_set_weighting(frt_handle h, const float *weight_db_host);
+/* The software-pipeline schedule of the fused-energy kernel for a stream of n_samples per channel
+ * processed in steps of 2^log2_chunk (5 or 6) samples: stage_start[10] = step at which stage j
+ * starts, *n_steps = steps until the pipeline has drained.  Pure host arithmetic (needs no GPU);
+ * exported so that tests/bank_pipeline_model.py can check the model against the library.       */
+int frt_bank_schedule(int n_octaves, int log2_chunk, int64_t n_samples, int *stage_start,
+                      int *n_steps);
 /* Process n_blocks consecutive blocks of `block` samples per channel
  * (x[c*x_stride + b*block + n]); block % 256 == 0 (the reference needs even lengths at every
  * stage, decimate.py:41).  State is carried across calls, so any blocking of a stream gives
@@ -106,7 +117,8 @@ int frt_bank_process(frt_handle h, const float *x_dev, int64_t x_stride, int blo
 /* State checkpoint / resume (the reference keeps its state inside the object,
  * octavefilters.py:50-56).  z: [C][n_octaves][2*bpo+6][2] section states; ema:
  * [C][n_octaves][bpo] smoothed energy divided by alpha_j (the kernel's internal form, so that a
- * get/set round trip is bit-exact).                                                          */
+ * get/set round trip is bit-exact).  The sections run in normalised form (numerator 1, c, 1; the
+ * chain gain is applied to the chain's output), z is the state of those sections.             */
 int frt_bank_state_size(frt_handle h, int64_t *z_floats, int64_t *ema_floats);
 int frt_bank_get_state(frt_handle h, float *z_host, float *ema_host);
 int frt_bank_set_state(frt_handle h, const float *z_host, const float *ema_host);

@@ -1,36 +1,40 @@
-#!/usr/bin/env python
-"""Quick timing of the filterbank kernel (not the bench contract): blocks/s for a few shapes."""
+"""Throughput of the filterbank kernels on the GPU box (tuning aid, not the bench):
+python tools/perf_bank.py [channels ...]"""
 import os
 import sys
+import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
+
 from friture_b200.octavefilters import Octave_Filters  # noqa: E402
 
 
-def run(C, block, nblocks, bpo=3, noct=9, reps=5):
-    x = torch.randn(C, block * nblocks, device="cuda") * 0.1
-    bank = Octave_Filters(bpo, n_octaves=noct)
-    bank.energies_batch(x, block=block)
+def run(C, block, nblk, noct, reps=5):
+    x = (torch.randn((C, block * nblk), dtype=torch.float32, device="cuda") * 0.1)
+    bank = Octave_Filters(3, n_octaves=noct)
+    bank.energies_batch(x, block=block, db=True)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
-        bank.energies_batch(x, block=block)
+        bank.energies_batch(x, block=block, db=True)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    bps = C * nblocks / (ms * 1e-3)
-    print("C=%5d block=%4d nblocks=%4d bpo=%2d noct=%2d: %8.3f ms  %.3e blocks/s  %.3e samples/s"
-          % (C, block, nblocks, bpo, noct, ms, bps, bps * block), flush=True)
+    return C * nblk / (ms * 1e-3), ms
 
 
 if __name__ == "__main__":
-    run(1024, 512, 256)
-    run(1024, 1024, 128)
-    run(1024, 256, 512)
-    run(1024, 512, 1)
-    run(8192, 512, 64)
-    run(256, 512, 256)
-    run(1024, 512, 256, noct=10)
-    run(1024, 512, 64, bpo=24)
+    chans = [int(v) for v in sys.argv[1:]] or [1024, 2048, 8192]
+    for C in chans:
+        for block, noct in ((512, 9), (1024, 10)):
+            nblk = 256 if block == 512 else 128
+            row = []
+            for kern, pack, logch in (("scan", 1, 5), ("pipe", 1, 5), ("pipe", 2, 5), ("pipe", 1, 6), ("pipe", 2, 6)):
+                os.environ["FRT_BANK_KERNEL"] = kern
+                os.environ["FRT_BANK_PACK"] = str(pack)
+                os.environ["FRT_BANK_LOGCH"] = str(logch)
+                r, ms = run(C, block, nblk, noct)
+                row.append("%s/p%d/c%d %.3g blk/s (%.2f ms)" % (kern, pack, 1 << logch, r, ms))
+            print("C=%d block=%d noct=%d nblk=%d: %s" % (C, block, noct, nblk, " | ".join(row)), flush=True)
