@@ -796,7 +796,7 @@ extern "C" int frt_bank_process(frt_handle h, const float *x_dev, int64_t x_stri
     if (force_k && force_k[0] == 's') use_pipe = false;
     if (use_pipe) {
         int pack = pl->n_channels >= 2048 ? 2 : 1;
-        int logch = (block >= 512 && n_blocks >= 8) ? 6 : 5;
+        int logch = block >= 512 ? 6 : 5;   // must not depend on n_blocks: a stream gives the same bits however it is cut into launches
         if (force_p) pack = force_p[0] == '2' ? 2 : 1;
         if (force_c) logch = force_c[0] == '6' ? 6 : 5;
         if (block < (1 << logch) * 4) logch = 5;

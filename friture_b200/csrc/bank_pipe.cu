@@ -5,40 +5,46 @@
 // friture/signal/decimate.py:39-41, fused with exp_smoothed_value(y**2),
 // friture/octavespectrum.py:104 / friture/signal/exp_smoothing.py:11-56), different schedule:
 //
-// ONE WARP PER CHANNEL (or per channel PAIR, two channels packed in float2 -> FFMA2), and inside
-// the warp ONE LANE PER BIQUAD SECTION.  A recursion is serial in time, so instead of splitting
-// time (bank.cu: two passes + a scan per section) every lane runs ITS section serially over a
-// chunk of CH samples per step and hands the chunk to the next section of its chain through a
-// shared-memory ring; the chain is a software pipeline, lane r works on the chunk lane r-1
-// finished one step earlier.  Each sample of each section is computed exactly once, with the
-// 4-operation normalised biquad (bank_internal.cuh).
+// A recursion is serial in time, so instead of splitting time (bank.cu: two passes + a scan per
+// section) the SECTIONS are spread over lanes and every lane runs its sections serially over a chunk
+// of CH samples per step, handing the chunk to the next lane of its chain through a shared-memory
+// ring: the chain is a software pipeline, a lane works on the chunk its predecessor finished one
+// step earlier.  Each sample of each section is computed exactly once, with the 4-operation
+// normalised biquad (bank_internal.cuh).
 //
-//   lanes [0, NSEC)       sections of stage 0 (rate fs):  bands (2 sections each), 6 decimator
-//   lanes [NSEC, 2 NSEC)  the same sections for ALL lower-rate stages, time-multiplexed: of the
-//                         CH sample slots of a step, slots [CH-2 len_j, CH-len_j) belong to stage
-//                         j (len_j = CH >> j) and the last slot to the one stage >= JR = log2(CH)+1
-//                         whose turn it is (stage JR + ctz(u+1): a binary-ruler schedule, every
-//                         stage gets exactly its 2^-j share) -- 31/32 of these lanes' slots are used.
-//   The last decimator lane keeps the even samples (x gain) and writes them where the next
-//   stage's chain heads will read them one step later (slot i -> CH/2 + i/2 of the multiplexed
-//   input vector; single samples of the ruler stages wait in a per-stage mailbox).
-//   Smoothing of y^2 is NOT done in the section loops: after each step all 32 lanes update one
-//   accumulator per sample slot (acc <- q^len acc + y^2, 3 instructions per band per step instead
-//   of 2 per sample); at a block end the accumulators of a stage are combined with a weighted
-//   (segmented) warp reduction into the band energy and collapsed back to one value, so the state
-//   carried between launches is the plain smoothed energy.  Decays are applied in complement form
-//   (acc - (1-q^n) acc) so that the float32 rounding of q does not bias long time constants.
+// One HALF-WARP per channel (per channel pair when two channels are packed in float2 -> FFMA2),
+// NR = bpo + 3 roles per lane group, TWO CHAINED SECTIONS PER LANE (their recurrences are
+// independent, which gives the in-order issue two chains to interleave):
+//   role r < bpo      band r: both band-pass sections, reads the stage input
+//   role bpo + d      decimator sections 2d, 2d+1 (d = 0, 1, 2); d = 0 reads the stage input
+//   lanes [0, NR)     group 0: stage 0 (rate fs)
+//   lanes [NR, 2 NR)  group 1: the same roles for ALL lower-rate stages, time-multiplexed: of the
+//                     CH sample slots of a step, slots [CH-2 len_j, CH-len_j) belong to stage j
+//                     (len_j = CH >> j) and the last slot to the one stage >= JR = log2(CH)+1 whose
+//                     turn it is (stage JR + ctz(u+1): a binary-ruler schedule, every stage gets
+//                     exactly its 2^-j share) -- 31/32 of these lanes' slots carry work.
+//   The last decimator lane keeps the even samples (x chain gain) and writes them where the next
+//   stage's chain heads read them one step later (slot i -> CH/2 + i/2 of the multiplexed input
+//   vector; the single samples of the ruler stages wait in a double-buffered per-stage mailbox).
+//   Smoothing of y^2 is NOT done in the section loops: after each step the 16 lanes of the
+//   half-warp update one accumulator per sample slot (acc <- q^len acc + y^2, a few instructions
+//   per band per step instead of two per sample); at a block end the accumulators of a stage are
+//   combined with a weighted warp reduction into the band energy and collapsed back to one value, so
+//   the state carried between launches is the plain smoothed energy and a stream gives the same
+//   bits whether it arrives in one launch or block by block.  Decays are applied in complement
+//   form (acc - (1-q^n) acc): the float32 rounding of q must not bias long time constants.
 //
 // tests/bank_pipeline_model.py is an executable NumPy model of exactly this schedule, checked
 // against the oracle on CPU; this file mirrors it phase by phase.
 #include <cmath>
 #include <cstdlib>
+#include <type_traits>
 
 #include "bank_internal.cuh"
 
 namespace {
 
-constexpr int DEC_SECTIONS = 6;
+constexpr int DEC_DEPTH = 3;     // decimator chain = 3 lanes: a stage trails its parent by 3 steps
 
 template <int PACK> struct VT;
 template <> struct VT<1> { using t = float; };
@@ -60,6 +66,10 @@ __device__ __forceinline__ float v_x(float a) { return a; }
 __device__ __forceinline__ float v_x(float2 a) { return a.x; }
 __device__ __forceinline__ float v_y(float a) { return a; }
 __device__ __forceinline__ float v_y(float2 a) { return a.y; }
+__device__ __forceinline__ float v_sel(bool p, float a, float b) { return p ? a : b; }
+__device__ __forceinline__ float2 v_sel(bool p, float2 a, float2 b) {
+    return make_float2(p ? a.x : b.x, p ? a.y : b.y);
+}
 __device__ __forceinline__ float v_shfl_xor(float a, int d) { return __shfl_xor_sync(0xffffffffu, a, d); }
 __device__ __forceinline__ float2 v_shfl_xor(float2 a, int d) {
     return make_float2(__shfl_xor_sync(0xffffffffu, a.x, d), __shfl_xor_sync(0xffffffffu, a.y, d));
@@ -88,25 +98,14 @@ __device__ __forceinline__ void st2(float *p, float a, float b) {
 __device__ __forceinline__ void st2(float2 *p, float2 a, float2 b) {
     *reinterpret_cast<float4 *>(p) = make_float4(a.x, a.y, b.x, b.y);
 }
-// (z1, z2) of one section: 2 T's, 8*PACK bytes, aligned
-__device__ __forceinline__ void ldz(const float *p, float &z1, float &z2) {
-    const float2 t = *reinterpret_cast<const float2 *>(p);
-    z1 = t.x; z2 = t.y;
-}
-__device__ __forceinline__ void ldz(const float2 *p, float2 &z1, float2 &z2) {
-    const float4 t = *reinterpret_cast<const float4 *>(p);
-    z1 = make_float2(t.x, t.y); z2 = make_float2(t.z, t.w);
-}
-__device__ __forceinline__ void stz(float *p, float z1, float z2) {
-    *reinterpret_cast<float2 *>(p) = make_float2(z1, z2);
-}
-__device__ __forceinline__ void stz(float2 *p, float2 z1, float2 z2) {
-    *reinterpret_cast<float4 *>(p) = make_float4(z1.x, z1.y, z2.x, z2.y);
-}
 
 __device__ __forceinline__ void cp_async4(void *smem, const void *gmem) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() {
@@ -128,9 +127,8 @@ __device__ __forceinline__ float energy_out(float e, int kband, const BankArgs &
 }
 
 template <class T>
-__device__ __forceinline__ void emit(const BankArgs &a, float alpha_j, T val, int ch0, bool has2,
-                                     int blk, int kband, int nbands) {
-    if (!a.energies) return;
+__device__ __noinline__ void emit(const BankArgs &a, float alpha_j, T val, int ch0, bool has2,
+                                  int blk, int kband, int nbands) {
     float *o = a.energies + ((size_t)ch0 * a.n_blocks + blk) * nbands + kband;
     o[0] = energy_out(alpha_j * v_x(val), kband, a);
     if (sizeof(T) == 8 && has2) o[(size_t)a.n_blocks * nbands] = energy_out(alpha_j * v_y(val), kband, a);
@@ -146,30 +144,62 @@ __device__ __forceinline__ T biquad(T x, T &z1, T &z2, float cc, float na1, floa
     return y;
 }
 
+// Sample slots of a step are grouped in segments (= stages of the multiplexed lanes): segment
+// g < LOGCH holds the CH >> (g+1) slots starting at CH - 2 (CH >> (g+1)), segment LOGCH is the
+// ruler slot CH-1.  A segment starts at slot s >= CH/2 whenever CH - s is a power of two, and is
+// then segment LOGCH - log2(CH - s).
+__host__ __device__ constexpr int ilog2c(int v) {
+    return v >= 64 ? 6 : v >= 32 ? 5 : v >= 16 ? 4 : v >= 8 ? 3 : v >= 4 ? 2 : v >= 2 ? 1 : 0;
+}
+__host__ __device__ constexpr bool seg_starts_at(int slot, int ch) {
+    return slot >= ch / 2 && ((ch - slot) & (ch - slot - 1)) == 0;
+}
+
+template <int LOGCH, int PACK, int BPO>
+struct PipeLayout {     // shared memory of one channel slot (half-warp), in units of T
+    static constexpr int CH = 1 << LOGCH;
+    static constexpr int NR = BPO + DEC_DEPTH;
+    static constexpr int TB = 4 * PACK;                       // bytes per T
+    static constexpr int PAD = 16 / TB;                       // 16 B of bank skew between buffers
+    static constexpr int X = 0;                               // [RX][2 CH]
+    static constexpr int L = X + PIPE_RX * 2 * CH;            // [2 groups][2 links][2 bufs][CH + PAD]
+    static constexpr int LBUF = CH + PAD;
+    static constexpr int BO = L + 8 * LBUF;                   // [2 groups][BPO][CH + PAD]
+    static constexpr int S = BO + 2 * BPO * LBUF;             // [MAX_OCT][NR][4]: z1A z2A z1B z2B
+    static constexpr int ER = S + BANK_MAX_OCT * NR * 4;      // [MAX_OCT][4]: ruler-stage energies
+    static constexpr int MB = ER + BANK_MAX_OCT * 4;          // [MAX_OCT + 2][2] mailboxes
+    static constexpr int TOTAL = MB + (BANK_MAX_OCT + 2) * 2;
+    static_assert(TOTAL % PAD == 0 || PAD == 1, "16-byte multiple");
+};
+
 template <int LOGCH, int PACK, int BPO>
 __global__ void __launch_bounds__(32)
 bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
     using T = typename VT<PACK>::t;
-    constexpr int CH = 1 << LOGCH, JR = LOGCH + 1, NSEC = 2 * BPO + DEC_SECTIONS, NL = 2 * NSEC;
-    constexpr int SPL = CH / 32;
+    using LY = PipeLayout<LOGCH, PACK, BPO>;
+    constexpr int CH = 1 << LOGCH, JR = LOGCH + 1, NR = LY::NR, NSEC = 2 * NR;
+    constexpr int NSL = CH / 16;              // sample slots per lane of the half-warp (phase B)
+    constexpr int NG = CH / 4;                // 4-sample groups per step
+    constexpr int GB = (PACK == 1 ? 32 : 16) / 4;   // groups whose inputs are loaded ahead
     constexpr int RX = PIPE_RX, PF = PIPE_PF;
-    constexpr int LPAD = 16 / (int)sizeof(T);
-    constexpr int LSTR = 2 * CH + LPAD;       // per-lane output ring: 2 chunks + 16 B of bank skew
-    static_assert(NL <= 32, "two lane groups must fit in a warp");
+    static_assert(2 * NR <= 16, "two lane groups must fit in a half-warp");
     static_assert(LOGCH == 5 || LOGCH == 6, "steps of 32 or 64 samples");
-    constexpr unsigned FULL = 0xffffffffu;
+    static_assert(NG % GB == 0, "whole load batches");
 
     extern __shared__ float4 smem4[];
-    T *sX = reinterpret_cast<T *>(smem4);             // [RX][2 CH]: stage-0 chunk | multiplexed vector
-    T *sL = sX + RX * 2 * CH;                         // [NL][LSTR]
-    T *sS = sL + NL * LSTR;                           // [MAX_OCT][NSEC][4]: z1 z2 e -
-    T *sMB = sS + BANK_MAX_OCT * NSEC * 4;            // [MAX_OCT + 1] mailboxes of the ruler stages
-    int *sT = reinterpret_cast<int *>(sMB + 12);      // [MAX_OCT + 1]
-    float *sAl = reinterpret_cast<float *>(sT + 12);  // [MAX_OCT + 1]
-
     const int lane = threadIdx.x;
-    const int ch0 = blockIdx.x * PACK;
-    const bool has2 = (PACK == 2) && (ch0 + 1 < a.n_channels);
+    const int h = lane >> 4, hl = lane & 15;
+    T *sm = reinterpret_cast<T *>(smem4) + h * LY::TOTAL;       // this half-warp's channel slot
+    int *sT = reinterpret_cast<int *>(reinterpret_cast<T *>(smem4) + 2 * LY::TOTAL);   // [MAX_OCT + 2]
+    float *sAl = reinterpret_cast<float *>(sT + 12);            // [MAX_OCT + 2]
+    T *sX = sm + LY::X, *sL = sm + LY::L, *sBO = sm + LY::BO, *sS = sm + LY::S, *sER = sm + LY::ER,
+      *sMB = sm + LY::MB;
+
+    // channels of this half-warp (clamped when the last warp is not full; `alive` gates the writes)
+    const int cgrp = blockIdx.x * 2 + h;
+    const bool alive = cgrp * PACK < a.n_channels;
+    const int ch0 = alive ? cgrp * PACK : 0;
+    const bool has2 = (PACK == 2) && alive && (ch0 + 1 < a.n_channels);
     const int ch1 = has2 ? ch0 + 1 : ch0;
     const int n_oct = P.n_oct;
     const int nbands = n_oct * BPO;
@@ -177,58 +207,59 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
     const int lognb = 31 - __clz(a.block) - LOGCH;          // block = CH << lognb
     const int nbmask = (1 << lognb) - 1;
     const int logblock = lognb + LOGCH;
+    const bool want_e = alive && a.energies != nullptr;
 
-    // ---- lane roles
-    const bool worker = lane < NL;
-    const int G = worker ? lane / NSEC : 0;
-    const int r = worker ? lane - G * NSEC : 0;
-    const bool isband = r < 2 * BPO;
-    const int s = isband ? (r & 1) : r - 2 * BPO;            // position in the chain = skew
-    const bool isdec5 = (r == NSEC - 1);
+    // ---- lane roles (phase A)
+    const bool worker = hl < 2 * NR;
+    const int G = (worker && hl >= NR) ? 1 : 0;
+    const int r = worker ? hl - G * NR : 0;
+    const bool isband = r < BPO;
+    const int d = isband ? 0 : r - BPO;                      // skew = position in the decimator chain
+    const bool isdec2 = worker && (r == NR - 1);
+    const bool ishead = (d == 0);                            // reads the stage input
     const int maxstage = isband ? n_oct - 1 : n_oct - 2;     // the last stage's decimator is unused (filter.py:113)
-    const bool isemar = (G == 1) && isband && (s == 1);      // smooths the ruler stages in the lane
-    const float cc = P.c[r], na1 = P.na1[r], na2 = P.na2[r];
-    const float gb_lane = isband ? P.gband[r >> 1] : 0.f;
+    const float cA = P.c[2 * r], n1A = P.na1[2 * r], n2A = P.na2[2 * r];
+    const float cB = P.c[2 * r + 1], n1B = P.na1[2 * r + 1], n2B = P.na2[2 * r + 1];
+    const float gb_lane = isband ? P.gband[r] : 0.f;
     const float gdec = P.gdec;
 
     // ---- prologue: tables, state
-    if (lane <= BANK_MAX_OCT) {
-        sT[lane] = P.T[lane];
-        sAl[lane] = P.alpha[lane];
+    if (lane <= BANK_MAX_OCT + 1) {
+        sT[lane] = lane <= BANK_MAX_OCT ? P.T[lane] : 0x3fffffff;
+        sAl[lane] = lane <= BANK_MAX_OCT ? P.alpha[lane] : 1.f;
     }
-    const float *gz0 = a.zstate + (size_t)ch0 * n_oct * NSEC * 2;
-    const float *gz1 = a.zstate + (size_t)ch1 * n_oct * NSEC * 2;
+    float *gz0 = a.zstate + (size_t)ch0 * n_oct * NSEC * 2;
+    float *gz1 = a.zstate + (size_t)ch1 * n_oct * NSEC * 2;
     float *ge0 = a.ema + (size_t)ch0 * nbands;
     float *ge1 = a.ema + (size_t)ch1 * nbands;
-    for (int i = lane; i < BANK_MAX_OCT * NSEC; i += 32) {
-        const int j = i / NSEC, rr = i - j * NSEC;
-        T z1, z2, e;
-        v_set(z1, 0.f, 0.f); v_set(z2, 0.f, 0.f); v_set(e, 0.f, 0.f);
-        if (j < n_oct) {
-            v_set(z1, gz0[2 * i], gz1[2 * i]);
-            v_set(z2, gz0[2 * i + 1], gz1[2 * i + 1]);
-            if (j >= JR && rr < 2 * BPO && (rr & 1)) v_set(e, ge0[j * BPO + (rr >> 1)], ge1[j * BPO + (rr >> 1)]);
-        }
-        sS[i * 4 + 0] = z1; sS[i * 4 + 1] = z2; sS[i * 4 + 2] = e; sS[i * 4 + 3] = e;
+    for (int i = hl; i < BANK_MAX_OCT * NSEC * 2; i += 16) {    // sS[j][r][4] == global z[j][2r .. 2r+1][2]
+        T z;
+        v_set(z, 0.f, 0.f);
+        if (i < n_oct * NSEC * 2) v_set(z, gz0[i], gz1[i]);
+        sS[i] = z;
     }
-    // smoothing accumulators: one per sample slot (slot = lane + 32 s) of the two band-output vectors
-    T acc0[BPO][SPL], accm[BPO][SPL];
-    int Tm[SPL], mst[SPL], gsz[SPL];
-    bool mok[SPL], lastslot[SPL], firstslot[SPL];
-    float om0[SPL], aqm[SPL], omm[SPL];
+    for (int i = hl; i < BANK_MAX_OCT * 4; i += 16) {
+        const int j = i >> 2, b = i & 3;
+        T e;
+        v_set(e, 0.f, 0.f);
+        if (j >= JR && j < n_oct && b < BPO) v_set(e, ge0[j * BPO + b], ge1[j * BPO + b]);
+        sER[i] = e;
+    }
+    // smoothing accumulators: one per sample slot (slot = hl + 16 q) of the two band-output vectors
+    T acc0[BPO][NSL], accm[BPO][NSL];
+    int mst[NSL];
+    bool mok[NSL], lastslot[NSL];
+    float om0[NSL], aqm[NSL], omm[NSL];
 #pragma unroll
-    for (int q = 0; q < SPL; q++) {
-        const int p = lane + 32 * q;
+    for (int q = 0; q < NSL; q++) {
+        const int p = hl + 16 * q;
         const int j = 1 + __clz(~((unsigned)p << (32 - LOGCH)));     // stage owning slot p
         mst[q] = j;
         mok[q] = (j < JR) && (j <= n_oct - 1);
-        gsz[q] = CH >> j;
-        Tm[q] = P.T[j < BANK_MAX_OCT ? j : BANK_MAX_OCT];
-        firstslot[q] = (p == CH - 2 * (CH >> j));
         lastslot[q] = (p == CH - (CH >> j) - 1);
-        om0[q] = P.om0[q][lane];
-        aqm[q] = P.aqm[q][lane];
-        omm[q] = P.omm[q][lane];
+        om0[q] = P.om0[p >> 5][p & 31];
+        aqm[q] = P.aqm[p >> 5][p & 31];
+        omm[q] = P.omm[p >> 5][p & 31];
 #pragma unroll
         for (int b = 0; b < BPO; b++) {
             v_set(acc0[b][q], 0.f, 0.f);
@@ -239,15 +270,20 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
     }
     const float *x0 = a.x + (size_t)ch0 * a.x_stride;
     const float *x1 = a.x + (size_t)ch1 * a.x_stride;
+    const bool vec16 = (PACK == 1) && a.vec_ok;
     auto prefetch = [&](int cn) {
         if (cn < n_chunks) {
             T *dst = sX + (cn & (RX - 1)) * 2 * CH;
+            if (vec16) {
+                if (hl < CH / 4) cp_async16(dst + 4 * hl, x0 + (size_t)cn * CH + 4 * hl);
+            } else {
 #pragma unroll
-            for (int q = 0; q < SPL; q++) {
-                const int p = lane + 32 * q;
-                float *d = reinterpret_cast<float *>(dst + p);
-                cp_async4(d, x0 + (size_t)cn * CH + p);
-                if (PACK == 2) cp_async4(d + 1, x1 + (size_t)cn * CH + p);
+                for (int q = 0; q < NSL; q++) {
+                    const int p = hl + 16 * q;
+                    float *dd = reinterpret_cast<float *>(dst + p);
+                    cp_async4(dd, x0 + (size_t)cn * CH + p);
+                    if (PACK == 2) cp_async4(dd + 1, x1 + (size_t)cn * CH + p);
+                }
             }
         }
         cp_async_commit();
@@ -258,236 +294,290 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
     __syncwarp();
 
     // stage-0 lanes carry their section state in registers from step to step
-    T zc1 = sS[r * 4 + 0], zc2 = sS[r * 4 + 1];
-    const int sstep = G ? NSEC * 4 : 0;                     // T elements per stage row of sS
-    const int tstep = G ? DEC_SECTIONS : 0;                 // T[j] = 6 j for the chunked stages
+    T zc[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) zc[i] = sS[r * 4 + i];
     const int n_steps = a.n_steps;
+    // steps in [k_lo, k_hi) have every slot of every lane valid (pipeline full, nothing drained):
+    // they run the variant without the range checks
+    const int k_lo = P.T[n_oct - 1] + DEC_DEPTH;
+    const int k_hi = (n_oct > JR) ? n_chunks : 0;
 
-    for (int k = 0; k < n_steps; k++) {
-        // ============================================================ phase A: the section loops
-        if (worker) {
-            const int u = k - s;
-            const T *inp = (s == 0) ? sX + (k & (RX - 1)) * 2 * CH + G * CH
-                                    : sL + (lane - 1) * LSTR + ((k - 1) & 1) * CH;
-            T *outp = sL + lane * LSTR + (k & 1) * CH;
-            T *xn = sX + ((k + 1) & (RX - 1)) * 2 * CH + CH + G * (CH / 2);
-            T *sp = sS + r * 4;
-            int cidx = u;
-            T z1 = zc1, z2 = zc2;
-            const bool pv0 = (unsigned)u < (unsigned)n_chunks && 0 <= maxstage;
-            // ---- segments of 4 or more samples: stage G*(g+1), slots [CH - 2 len, CH - len)
+    // ================================================================ phase A: the section loops
+    auto phaseA = [&](int k, auto check_tag) {
+        constexpr bool CHECK = decltype(check_tag)::value;
+        const int u = k - d;
+        const T *inp = ishead ? sX + (k & (RX - 1)) * 2 * CH + G * CH
+                              : sL + ((G * 2 + d - 1) * 2 + ((k - 1) & 1)) * LY::LBUF;
+        T *outp = isband ? sBO + (G * BPO + r) * LY::LBUF
+                         : sL + ((G * 2 + d) * 2 + (k & 1)) * LY::LBUF;
+        T *xn = sX + ((k + 1) & (RX - 1)) * 2 * CH + CH + G * (CH / 2);
+        const bool pv0 = !CHECK || ((unsigned)u < (unsigned)n_chunks && 0 <= maxstage);
+        // ruler slot: the stage >= JR whose sample is due (group 1 only)
+        const int jr = JR - 1 + __ffs(u + 1);
+        const int jrc = jr < BANK_MAX_OCT - 1 ? jr : BANK_MAX_OCT - 1;
+        const int Tj = sT[jrc];
+        const int m = (u - Tj) >> (jrc - LOGCH);
+        bool pvR = jr <= maxstage;
+        if (CHECK) pvR = pvR && u >= Tj && m < (int)(a.t_total >> jrc);
+
+        // section state: group 0 keeps it in registers (zc); group 1 switches rows of sS at every
+        // segment start, the next row is fetched one segment ahead
+        T cur[4], nxt[4];
 #pragma unroll
-            for (int g = 0; g <= LOGCH - 3; g++) {
-                const int len = CH >> (g + 1), off = CH - 2 * len;
-                sp += sstep;
-                cidx -= tstep;
-                const bool pv = (unsigned)cidx < (unsigned)n_chunks && (G ? g + 1 : 0) <= maxstage;
-                if (G) ldz(sp, z1, z2);
+        for (int i = 0; i < 4; i++) cur[i] = zc[i];
+        T *spc = sS + (1 * NR + r) * 4;        // state row of the segment being processed (group 1)
+        bool pvc = pv0;
+        if (G) {
 #pragma unroll
-                for (int q = 0; q < len / 4; q++) {
-                    T v[4], y[4];
-                    ld4(inp + off + 4 * q, v);
+            for (int i = 0; i < 4; i++) cur[i] = spc[i];
 #pragma unroll
-                    for (int i = 0; i < 4; i++) y[i] = biquad(v[i], z1, z2, cc, na1, na2);
-                    if (!isdec5) st4(outp + off + 4 * q, y);
-                    else st2(xn + (off + 4 * q) / 2, v_mul(gdec, y[0]), v_mul(gdec, y[2]));
-                }
-                if (G && pv) stz(sp, z1, z2);
+            for (int i = 0; i < 4; i++) nxt[i] = sS[(2 * NR + r) * 4 + i];
+            pvc = !CHECK || ((unsigned)(u - DEC_DEPTH) < (unsigned)n_chunks && 1 <= maxstage);
+        }
+        bool pvB = false;           // validity / chunk index of the 1-sample stage LOGCH (for the mailbox)
+        int cidxB = 0;
+#pragma unroll
+        for (int b0 = 0; b0 < NG; b0 += GB) {
+            T v[GB][4];
+#pragma unroll
+            for (int q = 0; q < GB; q++) ld4(inp + 4 * (b0 + q), v[q]);
+            if (b0 + GB == NG) {
+                // the ruler stage's sample comes from its mailbox, not from the ring
+                if (G && ishead) v[GB - 1][3] = sMB[jrc * 2 + (m & 1)];
             }
-            // ---- last group of 4 slots: a 2-sample stage, a 1-sample stage, the ruler slot
-            {
-                T v[4], y[4];
-                ld4(inp + CH - 4, v);
-                sp += sstep;
-                cidx -= tstep;
-                const bool pvA = (unsigned)cidx < (unsigned)n_chunks && (G ? LOGCH - 1 : 0) <= maxstage;
-                if (G) ldz(sp, z1, z2);
-                y[0] = biquad(v[0], z1, z2, cc, na1, na2);
-                y[1] = biquad(v[1], z1, z2, cc, na1, na2);
-                if (G && pvA) stz(sp, z1, z2);
-                sp += sstep;
-                cidx -= tstep;
-                const bool pvB = (unsigned)cidx < (unsigned)n_chunks && (G ? LOGCH : 0) <= maxstage;
-                const int cB = cidx;
-                if (G) ldz(sp, z1, z2);
-                y[2] = biquad(v[2], z1, z2, cc, na1, na2);
-                if (G && pvB) stz(sp, z1, z2);
-                // ruler slot: the stage >= JR whose sample is due (group 1); stage 0 for group 0
-                int jrc = 0, m = u;
-                bool pvR = pv0;
-                T e;
-                v_set(e, 0.f, 0.f);
-                T *spr = sS + r * 4;
-                if (G) {
-                    const int jr = JR - 1 + __ffs(u + 1);
-                    jrc = jr < BANK_MAX_OCT - 1 ? jr : BANK_MAX_OCT - 1;
-                    const int Tj = sT[jrc];
-                    m = (u - Tj) >> (jrc - LOGCH);
-                    pvR = jr <= maxstage && u >= Tj && m < (int)(a.t_total >> jrc);
-                    spr = sS + (jrc * NSEC + r) * 4;
-                    ldz(spr, z1, z2);
-                    e = spr[2];
-                }
-                y[3] = biquad(v[3], z1, z2, cc, na1, na2);
-                if (G && pvR) stz(spr, z1, z2);
-                if (isemar) {
-                    // exp_smoothed_value of the low-rate stages: e <- (1-alpha) e + y^2 (e/alpha form)
-                    const float alj = sAl[jrc];
-                    const T yy = v_mul(gb_lane, y[3]);
-                    e = v_add(v_fma(-alj, e, e), v_sq(yy));
-                    if (pvR) {
-                        spr[2] = e;
-                        const int bl = logblock - jrc;           // block >> jrc = 2^bl samples
-                        if (((m + 1) & ((1 << bl) - 1)) == 0)
-                            emit<T>(a, alj, e, ch0, has2, ((m + 1) >> bl) - 1,
-                                    (n_oct - 1 - jrc) * BPO + (r >> 1), nbands);
+#pragma unroll
+            for (int q = 0; q < GB; q++) {
+                T y[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int slot = 4 * (b0 + q) + i;
+                    if (seg_starts_at(slot, CH)) {
+                        // group 1 switches to the state of the next stage; group 0 keeps its registers
+                        const int g = LOGCH - ilog2c(CH - slot);
+                        if (G) {
+                            if (pvc) {
+#pragma unroll
+                                for (int e = 0; e < 4; e++) spc[e] = cur[e];
+                            }
+#pragma unroll
+                            for (int e = 0; e < 4; e++) cur[e] = nxt[e];
+                            spc = (g < LOGCH) ? sS + ((g + 1) * NR + r) * 4 : sS + (jrc * NR + r) * 4;
+                            if (g < LOGCH) {
+                                const T *spn = (g + 1 < LOGCH) ? sS + ((g + 2) * NR + r) * 4
+                                                               : sS + (jrc * NR + r) * 4;
+#pragma unroll
+                                for (int e = 0; e < 4; e++) nxt[e] = spn[e];
+                                pvc = !CHECK || ((unsigned)(u - DEC_DEPTH * (g + 1)) < (unsigned)n_chunks &&
+                                                 (g + 1) <= maxstage);
+                                if (g == LOGCH - 1) {
+                                    pvB = pvc;
+                                    cidxB = u - DEC_DEPTH * (g + 1);
+                                }
+                            } else {
+                                pvc = pvR;
+                            }
+                        }
                     }
+                    const T ya = biquad(v[q][i], cur[0], cur[1], cA, n1A, n2A);
+                    y[i] = biquad(ya, cur[2], cur[3], cB, n1B, n2B);
                 }
-                if (!isdec5) {
-                    st4(outp + CH - 4, y);
+                const int gq = b0 + q;
+                if (gq < NG - 1) {
+                    if (!isdec2) st4(outp + 4 * gq, y);
+                    else st2(xn + 2 * gq, v_mul(gdec, y[0]), v_mul(gdec, y[2]));
                 } else {
-                    xn[(CH - 4) / 2] = v_mul(gdec, y[0]);
-                    if (!G) {
-                        xn[(CH - 2) / 2] = v_mul(gdec, y[2]);
+                    // last group: slots CH-4, CH-3 (a 2-sample stage), CH-2 (a 1-sample stage), CH-1 (ruler)
+                    if (!isdec2) {
+                        st4(outp + 4 * gq, y);
                     } else {
-                        if (pvB && !(cB & 1)) sMB[JR] = v_mul(gdec, y[2]);
-                        if (pvR && !(m & 1)) sMB[jrc + 1] = v_mul(gdec, y[3]);
+                        xn[2 * gq] = v_mul(gdec, y[0]);
+                        if (!G) {
+                            xn[2 * gq + 1] = v_mul(gdec, y[2]);
+                        } else {
+                            if (pvB && !(cidxB & 1)) sMB[JR * 2 + ((cidxB >> 1) & 1)] = v_mul(gdec, y[2]);
+                            if (pvR && !(m & 1)) sMB[(jrc + 1) * 2 + ((m >> 1) & 1)] = v_mul(gdec, y[3]);
+                        }
+                    }
+                    if (G && isband) {
+                        // exp_smoothed_value of the low-rate stages: e <- (1-alpha) e + y^2 (e/alpha form)
+                        const float alj = sAl[jrc];
+                        T e = sER[jrc * 4 + r];
+                        const T yy = v_mul(gb_lane, y[3]);
+                        e = v_add(v_fma(-alj, e, e), v_sq(yy));
+                        if (pvR) {
+                            sER[jrc * 4 + r] = e;
+                            const int bl = logblock - jrc;           // block >> jrc = 2^bl samples
+                            if (want_e && ((m + 1) & ((1 << bl) - 1)) == 0)
+                                emit<T>(a, alj, e, ch0, has2, ((m + 1) >> bl) - 1,
+                                        (n_oct - 1 - jrc) * BPO + r, nbands);
+                        }
                     }
                 }
-                if (!G && pv0) { zc1 = z1; zc2 = z2; }
             }
         }
-        __syncwarp();
-        // ============================================================ phase B: smoothing, prefetch
-        {
-            const int c0i = k - 1;
-            const bool valid0 = (unsigned)c0i < (unsigned)n_chunks;
-            const bool end0 = valid0 && (((c0i + 1) & nbmask) == 0);
-            bool vm[SPL], em[SPL];
-            int cmv[SPL];
-            bool anyend = false;
+        if (G) {
+            if (pvc) {
 #pragma unroll
-            for (int q = 0; q < SPL; q++) {
-                cmv[q] = k - 1 - Tm[q];
-                vm[q] = mok[q] && (unsigned)cmv[q] < (unsigned)n_chunks;
-                em[q] = vm[q] && (((cmv[q] + 1) & nbmask) == 0);
-                anyend = anyend || em[q];
+                for (int e = 0; e < 4; e++) spc[e] = cur[e];
             }
-            const int buf = (k & 1) * CH;
+        } else if (pv0) {
+#pragma unroll
+            for (int e = 0; e < 4; e++) zc[e] = cur[e];
+        }
+    };
+
+    // ================================================================ phase B: smoothing, prefetch
+    auto phaseB = [&](int k, auto check_tag) {
+        constexpr bool CHECK = decltype(check_tag)::value;
+        const bool valid0 = !CHECK || (unsigned)k < (unsigned)n_chunks;
+        bool vm[NSL];
+#pragma unroll
+        for (int q = 0; q < NSL; q++) {
+            vm[q] = mok[q];
+            if (CHECK) vm[q] = vm[q] && (unsigned)(k - DEC_DEPTH * mst[q]) < (unsigned)n_chunks;
+        }
+#pragma unroll
+        for (int b = 0; b < BPO; b++) {
+            const T *y0p = sBO + b * LY::LBUF;
+            const T *ymp = sBO + (BPO + b) * LY::LBUF;
+            const float gb = P.gband[b];
+#pragma unroll
+            for (int q = 0; q < NSL; q++) {
+                const int p = hl + 16 * q;
+                const T yy = v_mul(gb, y0p[p]);
+                const T ym = v_mul(gb, ymp[p]);
+                if (valid0) acc0[b][q] = v_add(v_fma(-P.aq0, acc0[b][q], acc0[b][q]), v_sq(yy));
+                if (vm[q]) accm[b][q] = v_add(v_fma(-aqm[q], accm[b][q], accm[b][q]), v_sq(ym));
+            }
+        }
+        // ---- block ends (warp-uniform conditions: they depend on the step only)
+        if (valid0 && (((k + 1) & nbmask) == 0)) {     // stage 0: weighted sum of its CH accumulators
+            const int blk = ((k + 1) >> lognb) - 1;
 #pragma unroll
             for (int b = 0; b < BPO; b++) {
-                const T *y0p = sL + (2 * b + 1) * LSTR + buf;
-                const T *ymp = sL + (NSEC + 2 * b + 1) * LSTR + buf;
-                const float gb = P.gband[b];
+                T val = v_fma(-om0[0], acc0[b][0], acc0[b][0]);
 #pragma unroll
-                for (int q = 0; q < SPL; q++) {
-                    const int p = lane + 32 * q;
-                    const T yy = v_mul(gb, y0p[p]);
-                    const T ym = v_mul(gb, ymp[p]);
-                    if (valid0) acc0[b][q] = v_add(v_fma(-P.aq0, acc0[b][q], acc0[b][q]), v_sq(yy));
-                    if (vm[q]) accm[b][q] = v_add(v_fma(-aqm[q], accm[b][q], accm[b][q]), v_sq(ym));
+                for (int q = 1; q < NSL; q++) val = v_add(val, v_fma(-om0[q], acc0[b][q], acc0[b][q]));
+#pragma unroll
+                for (int dlt = 8; dlt >= 1; dlt >>= 1) val = v_add(val, v_shfl_xor(val, dlt));
+#pragma unroll
+                for (int q = 0; q < NSL; q++) {
+                    v_set(acc0[b][q], 0.f, 0.f);
+                    if (hl + 16 * q == CH - 1) acc0[b][q] = val;
                 }
-            }
-            if (end0) {     // stage 0 finished a block: weighted sum of its CH accumulators
-                const int blk = ((c0i + 1) >> lognb) - 1;
-#pragma unroll
-                for (int b = 0; b < BPO; b++) {
-                    T val = v_fma(-om0[0], acc0[b][0], acc0[b][0]);
-#pragma unroll
-                    for (int q = 1; q < SPL; q++) val = v_add(val, v_fma(-om0[q], acc0[b][q], acc0[b][q]));
-#pragma unroll
-                    for (int dlt = 16; dlt >= 1; dlt >>= 1) val = v_add(val, v_shfl_xor(val, dlt));
-#pragma unroll
-                    for (int q = 0; q < SPL; q++) {
-                        v_set(acc0[b][q], 0.f, 0.f);
-                        if (lane + 32 * q == CH - 1) acc0[b][q] = val;
-                    }
-                    if (lane == 0) emit<T>(a, P.alpha[0], val, ch0, has2, blk, (n_oct - 1) * BPO + b, nbands);
-                }
-            }
-            if (__any_sync(FULL, anyend)) {   // some lower-rate stage finished a block
-#pragma unroll
-                for (int b = 0; b < BPO; b++) {
-#pragma unroll
-                    for (int q = 0; q < SPL; q++) {
-                        T val;
-                        v_set(val, 0.f, 0.f);
-                        if (em[q]) val = v_fma(-omm[q], accm[b][q], accm[b][q]);
-#pragma unroll
-                        for (int dlt = 1; dlt <= 16; dlt <<= 1) {
-                            const T t = v_shfl_xor(val, dlt);
-                            if (gsz[q] > dlt) val = v_add(val, t);
-                        }
-                        if (em[q]) {
-                            v_set(accm[b][q], 0.f, 0.f);
-                            if (lastslot[q]) accm[b][q] = val;
-                            if (firstslot[q])
-                                emit<T>(a, sAl[mst[q]], val, ch0, has2, ((cmv[q] + 1) >> lognb) - 1,
-                                        (n_oct - 1 - mst[q]) * BPO + b, nbands);
-                        }
-                    }
-                }
-            }
-            prefetch(k + PF);
-            cp_async_wait<PF - 1>();           // chunk k+1 has landed
-            if (lane == 0) {                   // the ruler stage of step k+1 reads its sample from the ring
-                const int jn = JR - 1 + __ffs(k + 2);
-                if (jn <= n_oct - 1) sX[((k + 1) & (RX - 1)) * 2 * CH + 2 * CH - 1] = sMB[jn];
+                if (hl == 0 && want_e) emit<T>(a, P.alpha[0], val, ch0, has2, blk, (n_oct - 1) * BPO + b, nbands);
             }
         }
+#pragma unroll
+        for (int j = 1; j <= LOGCH; j++) {             // chunked lower-rate stages
+            const int cm = k - DEC_DEPTH * j;
+            const bool ev = j <= n_oct - 1 && (unsigned)cm < (unsigned)n_chunks && (((cm + 1) & nbmask) == 0);
+            if (!ev) continue;
+            const int blk = ((cm + 1) >> lognb) - 1;
+            const int len = CH >> j, lo = CH - 2 * len;          // slots [lo, lo + len)
+            const int kb0 = (n_oct - 1 - j) * BPO;
+            if (len >= 16) {
+                // the stage fills whole registers q in [lo/16, (lo+len)/16): every lane takes part
+#pragma unroll
+                for (int b = 0; b < BPO; b++) {
+                    T val;
+                    v_set(val, 0.f, 0.f);
+#pragma unroll
+                    for (int q = lo / 16; q < (lo + len) / 16; q++)
+                        val = v_add(val, v_fma(-omm[q], accm[b][q], accm[b][q]));
+#pragma unroll
+                    for (int dlt = 8; dlt >= 1; dlt >>= 1) val = v_add(val, v_shfl_xor(val, dlt));
+#pragma unroll
+                    for (int q = lo / 16; q < (lo + len) / 16; q++) {
+                        v_set(accm[b][q], 0.f, 0.f);
+                        if (hl + 16 * q == lo + len - 1) accm[b][q] = val;
+                    }
+                    if (hl == 0 && want_e) emit<T>(a, sAl[j], val, ch0, has2, blk, kb0 + b, nbands);
+                }
+            } else {
+                // the stage sits in lanes [lo & 15, (lo & 15) + len) of the last register
+                constexpr int q = NSL - 1;
+                const int l0 = lo & 15;
+                const bool mine = hl >= l0 && hl < l0 + len;
+#pragma unroll
+                for (int b = 0; b < BPO; b++) {
+                    T val;
+                    v_set(val, 0.f, 0.f);
+                    if (mine) val = v_fma(-omm[q], accm[b][q], accm[b][q]);
+#pragma unroll
+                    for (int dlt = 1; dlt < 8; dlt <<= 1) {
+                        if (dlt < len) val = v_add(val, v_shfl_xor(val, dlt));
+                    }
+                    if (mine) {
+                        v_set(accm[b][q], 0.f, 0.f);
+                        if (hl == l0 + len - 1) accm[b][q] = val;
+                        if (hl == l0 && want_e) emit<T>(a, sAl[j], val, ch0, has2, blk, kb0 + b, nbands);
+                    }
+                }
+            }
+        }
+        prefetch(k + PF);
+        cp_async_wait<PF - 1>();           // chunk k+1 has landed
+    };
+
+    for (int k = 0; k < n_steps; k++) {
+        const bool fast = k >= k_lo && k < k_hi;
+        if (worker) {
+            if (fast) phaseA(k, std::false_type());
+            else phaseA(k, std::true_type());
+        }
+        __syncwarp();
+        if (fast) phaseB(k, std::false_type());
+        else phaseB(k, std::true_type());
         __syncwarp();
     }
 
     // ---- epilogue: the pipeline is drained, every stage ended on a block boundary
     if (worker && !G) {
-        sS[r * 4 + 0] = zc1;
-        sS[r * 4 + 1] = zc2;
+#pragma unroll
+        for (int i = 0; i < 4; i++) sS[r * 4 + i] = zc[i];
     }
     __syncwarp();
-    float *wz0 = a.zstate + (size_t)ch0 * n_oct * NSEC * 2;
-    float *wz1 = a.zstate + (size_t)ch1 * n_oct * NSEC * 2;
-    for (int i = lane; i < n_oct * NSEC; i += 32) {
-        const T z1 = sS[i * 4 + 0], z2 = sS[i * 4 + 1];
-        wz0[2 * i] = v_x(z1);
-        wz0[2 * i + 1] = v_x(z2);
-        if (has2) {
-            wz1[2 * i] = v_y(z1);
-            wz1[2 * i + 1] = v_y(z2);
+    if (alive) {
+        for (int i = hl; i < n_oct * NSEC * 2; i += 16) {
+            const T z = sS[i];
+            gz0[i] = v_x(z);
+            if (has2) gz1[i] = v_y(z);
         }
-    }
 #pragma unroll
-    for (int q = 0; q < SPL; q++) {
-        const int p = lane + 32 * q;
+        for (int q = 0; q < NSL; q++) {
+            const int p = hl + 16 * q;
 #pragma unroll
-        for (int b = 0; b < BPO; b++) {
-            if (p == CH - 1) {
-                ge0[b] = v_x(acc0[b][q]);
-                if (has2) ge1[b] = v_y(acc0[b][q]);
-            }
-            if (mok[q] && lastslot[q]) {
-                ge0[mst[q] * BPO + b] = v_x(accm[b][q]);
-                if (has2) ge1[mst[q] * BPO + b] = v_y(accm[b][q]);
+            for (int b = 0; b < BPO; b++) {
+                if (p == CH - 1) {
+                    ge0[b] = v_x(acc0[b][q]);
+                    if (has2) ge1[b] = v_y(acc0[b][q]);
+                }
+                if (mok[q] && lastslot[q]) {
+                    ge0[mst[q] * BPO + b] = v_x(accm[b][q]);
+                    if (has2) ge1[mst[q] * BPO + b] = v_y(accm[b][q]);
+                }
             }
         }
-    }
-    for (int i = lane; i < (n_oct - JR) * BPO; i += 32) {     // ruler stages
-        const int j = JR + i / BPO, b = i % BPO;
-        const T e = sS[(j * NSEC + 2 * b + 1) * 4 + 2];
-        ge0[j * BPO + b] = v_x(e);
-        if (has2) ge1[j * BPO + b] = v_y(e);
+        for (int i = hl; i < (n_oct - JR) * BPO; i += 16) {     // ruler stages
+            const int j = JR + i / BPO, b = i % BPO;
+            const T e = sER[j * 4 + b];
+            ge0[j * BPO + b] = v_x(e);
+            if (has2) ge1[j * BPO + b] = v_y(e);
+        }
     }
 }
 
 template <int LOGCH, int PACK, int BPO>
 cudaError_t launch_pipe(const PipeParams &P, const BankArgs &a, cudaStream_t st) {
-    constexpr int CH = 1 << LOGCH, NSEC = 2 * BPO + DEC_SECTIONS, NL = 2 * NSEC;
-    constexpr size_t TS = 4 * PACK;
-    constexpr size_t LSTR = 2 * CH + 16 / TS;
-    const size_t smem = TS * (PIPE_RX * 2 * CH + NL * LSTR + BANK_MAX_OCT * NSEC * 4 + 12) + 2 * 12 * 4;
+    using LY = PipeLayout<LOGCH, PACK, BPO>;
+    const size_t smem = (size_t)LY::TB * 2 * LY::TOTAL + 2 * 12 * 4;
     auto kern = bank_pipe_kernel<LOGCH, PACK, BPO>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const unsigned blocks = (unsigned)((a.n_channels + PACK - 1) / PACK);
+    const int per_warp = 2 * PACK;
+    const unsigned blocks = (unsigned)((a.n_channels + per_warp - 1) / per_warp);
     kern<<<blocks, 32, smem, st>>>(P, a);
     return cudaGetLastError();
 }
@@ -502,13 +592,13 @@ cudaError_t launch_pipe_bpo(const PipeParams &P, const BankArgs &a, cudaStream_t
 
 // Step at which the chain heads of stage j start (T[j]) and the number of steps that drains the
 // pipeline for t_total samples per channel.  Stages j <= logch move a chunk of 2^logch >> j samples
-// per step, six steps (the decimator chain) behind the previous stage; stage j > logch has one
+// per step, DEC_DEPTH steps (the decimator chain) behind the previous stage; stage j > logch has one
 // sample every P_j = 2^(j-logch) steps, at steps u = T_j (mod P_j) with T_j = P_j/2 - 1 (mod P_j),
 // which makes the stages' turns disjoint (the ruler sequence JR + ctz(u+1)).
 void frt_pipe_schedule(int n_oct, int logch, long long t_total, int *T, int *n_steps) {
     T[0] = 0;
     for (int j = 1; j <= BANK_MAX_OCT; j++) {
-        int t = T[j - 1] + DEC_SECTIONS;
+        int t = T[j - 1] + DEC_DEPTH;
         if (j > logch) {
             const int P = 1 << (j - logch), arem = P / 2 - 1;
             while (t % P != arem) t++;
@@ -519,7 +609,7 @@ void frt_pipe_schedule(int n_oct, int logch, long long t_total, int *T, int *n_s
     const long long n_chunks = t_total >> logch;
     long long last = 0;
     for (int j = 0; j < n_oct; j++) {
-        const int dmax = (j == n_oct - 1) ? 1 : DEC_SECTIONS - 1;
+        const int dmax = (j == n_oct - 1) ? 0 : DEC_DEPTH - 1;
         long long l;
         if (j <= logch) l = n_chunks - 1 + T[j] + dmax;
         else l = T[j] + (((t_total >> j) - 1) << (j - logch)) + dmax;

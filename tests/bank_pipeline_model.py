@@ -7,20 +7,20 @@ kernel mirrors this file phase by phase (phase A = the lanes' biquad loops, phas
 accumulators, block-end reductions, input prefetch, mailbox copy); the tests run it against
 oracle/friture_oracle.py on CPU.
 
-Layout of one warp (one channel):
-  lanes [0, NSEC)        group 0: section r = lane of stage 0
-  lanes [NSEC, 2*NSEC)   group 1: section r of stages >= 1, time-multiplexed: in the CH sample
-                         slots of one step, slots [CH-2*len_j, CH-len_j) belong to stage j
-                         (len_j = CH >> j, j = 1..LOGCH) and slot CH-1 to the one "ruler" stage
-                         JR + ctz(u+1) >= JR = LOGCH+1 that has a sample due
-  section r: r < 2*bpo -> band r//2, biquad r%2;  r >= 2*bpo -> decimator biquad r-2*bpo
-  skew d(r) = position in its chain: a lane works on the chunk the previous lane of its chain
-  finished one step earlier.
+Lanes of one channel (NR = bpo + 3 roles per group, two biquad sections chained per lane):
+  roles [0, NR)      group 0: stage 0 (rate fs)
+  roles [NR, 2*NR)   group 1: the same roles for ALL stages >= 1, time-multiplexed: in the CH sample
+                     slots of one step, slots [CH-2*len_j, CH-len_j) belong to stage j
+                     (len_j = CH >> j, j = 1..LOGCH) and slot CH-1 to the one "ruler" stage
+                     JR + ctz(u+1) >= JR = LOGCH+1 that has a sample due
+  role r < bpo: band r (both sections); role bpo+d: decimator sections 2d, 2d+1 (d = 0, 1, 2)
+  skew d: a decimator lane works on the chunk the previous lane of the chain finished one step
+  earlier; bands and the first decimator lane read the stage input directly.
 """
 import numpy as np
 
 MAX_OCT = 10
-DEC_SECTIONS = 6
+DEC_DEPTH = 3      # decimator chain = 3 lanes (2 sections each): a stage trails its parent by 3 steps
 
 
 def stage_start_steps(n_oct, logch):
@@ -29,7 +29,7 @@ def stage_start_steps(n_oct, logch):
     T = [0] * MAX_OCT
     jr = logch + 1
     for j in range(1, MAX_OCT):
-        t = T[j - 1] + DEC_SECTIONS
+        t = T[j - 1] + DEC_DEPTH
         if j >= jr:
             P = 1 << (j - logch)
             a = P // 2 - 1
@@ -45,7 +45,7 @@ def n_steps_for(n_oct, logch, t_total, T):
     n_chunks = t_total // ch
     last = 0
     for j in range(n_oct):
-        dmax = 1 if j == n_oct - 1 else DEC_SECTIONS - 1
+        dmax = 0 if j == n_oct - 1 else DEC_DEPTH - 1
         if j < jr:
             last = max(last, n_chunks - 1 + T[j] + dmax)
         else:
@@ -73,8 +73,9 @@ class PipeModel:
         self.logch = logch
         self.CH = 1 << logch
         self.JR = logch + 1
-        self.NSEC = 2 * self.bpo + DEC_SECTIONS
-        assert 2 * self.NSEC <= 32
+        self.NR = self.bpo + DEC_DEPTH
+        self.NSEC = 2 * self.NR
+        assert 2 * self.NR <= 16
         self.RX, self.PF = rx, pf
         self.alphas = np.ones(MAX_OCT)
         self.alphas[:n_oct] = np.asarray(alphas, dtype=np.float64)[:n_oct]
@@ -92,7 +93,6 @@ class PipeModel:
         self.z = np.zeros((n_oct, self.NSEC, 2))
         self.e = np.zeros((n_oct, self.bpo))
 
-    # ------------------------------------------------------------------ helpers
     def mux_stage_of_slot(self, p):
         """stage owning slot p of the multiplexed vector (p < CH-1)."""
         CH = self.CH
@@ -103,7 +103,7 @@ class PipeModel:
 
     def process(self, x, block):
         x = np.asarray(x, dtype=np.float64)
-        CH, JR, NSEC, bpo, n_oct, logch = self.CH, self.JR, self.NSEC, self.bpo, self.n_oct, self.logch
+        CH, JR, NR, bpo, n_oct, logch = self.CH, self.JR, self.NR, self.bpo, self.n_oct, self.logch
         RX, PF, T = self.RX, self.PF, self.T
         t_total = x.shape[0]
         assert block & (block - 1) == 0 and block >= 256 and t_total % block == 0
@@ -114,35 +114,24 @@ class PipeModel:
         n_steps = n_steps_for(n_oct, logch, t_total, T)
         nbands = n_oct * bpo
         energies = np.full((n_blocks, nbands), np.nan)
-        NL = 2 * NSEC
-        lanes = np.arange(32)
-        G = np.where(lanes < NL, lanes // NSEC, 2)
-        r = lanes % NSEC
-        active_lane = lanes < NL
-        isband = r < 2 * bpo
-        s = np.where(isband, r % 2, r - 2 * bpo)          # position in the chain = skew d
-        d = s
-        isdec5 = active_lane & (r == NSEC - 1)
-        maxstage = np.where(isband, n_oct - 1, n_oct - 2)
-        cc, na1, na2 = self.c[r], -self.a1[r], -self.a2[r]
+        # roles: lane = G*NR + r
+        NL = 2 * NR
         # shared memory
         X = np.full((RX, 2 * CH), np.nan)
-        L = np.full((32, 2, CH), np.nan)
-        S = np.zeros((MAX_OCT, NSEC, 3))                   # z1, z2, e (ruler stages, band s1 roles)
-        MB = np.full(MAX_OCT + 1, np.nan)
-        S[:n_oct, :, :2] = self.z
-        for j in range(JR, n_oct):
-            for b in range(bpo):
-                S[j, 2 * b + 1, 2] = self.e[j, b]
-        # phase-B accumulators, per slot of the two band-output vectors
+        L = np.full((NL, 2, CH), np.nan)                   # chain links (decimator lanes), 2 buffers
+        BO = np.full((2, bpo, CH), np.nan)                 # band outputs of this step, per group
+        S = np.zeros((MAX_OCT, NR, 4))                     # z1A z2A z1B z2B
+        ER = np.zeros((MAX_OCT, bpo))                      # smoothed energies of the ruler stages
+        MB = np.full((MAX_OCT + 1, 2), np.nan)             # mailboxes, double-buffered by sample parity
+        S[:n_oct] = self.z.reshape(n_oct, NR, 4)
+        ER[:n_oct] = self.e
         acc0 = np.zeros((bpo, CH))
         accm = np.zeros((bpo, CH))
         acc0[:, CH - 1] = self.e[0]
         slot_stage = np.array([self.mux_stage_of_slot(p) for p in range(CH - 1)] + [0])
-        for j in range(1, min(JR, n_oct)):
-            accm[:, CH - (CH >> j) - 1] = self.e[j]        # last slot of stage j's range
         len_of = lambda j: CH >> j
-        # weights: slot p of stage j's range at position pos: q_j^(len_j-1-pos)
+        for j in range(1, min(JR, n_oct)):
+            accm[:, CH - len_of(j) - 1] = self.e[j]        # last slot of stage j's range
         w0 = self.q[0] ** (CH - 1 - np.arange(CH))
         Q0 = self.q[0] ** CH
         wm = np.zeros(CH)
@@ -153,94 +142,103 @@ class PipeModel:
                 pos = p - (CH - 2 * len_of(j))
                 wm[p] = self.q[j] ** (len_of(j) - 1 - pos)
                 Qm[p] = self.q[j] ** len_of(j)
-        # prologue: prefetch chunks 0..PF-1
         for cpre in range(min(PF, n_chunks)):
             X[cpre % RX, :CH] = x[cpre * CH:(cpre + 1) * CH]
 
         def band_out(stage, b, val):
-            k = (n_oct - 1 - stage) * bpo + b
-            return k, self.alphas[stage] * val
+            return (n_oct - 1 - stage) * bpo + b, self.alphas[stage] * val
+
+        def sec_coefs(r):
+            i = 2 * r
+            return (self.c[i], -self.a1[i], -self.a2[i], self.c[i + 1], -self.a1[i + 1], -self.a2[i + 1])
 
         for k in range(n_steps):
             # ---------------------------------------------------------------- phase A
-            Lnew = {}
-            Xw = {}
-            MBw = {}
+            Lnew, Xw, MBw, BOw = {}, {}, {}, {}
             for lane in range(NL):
-                g, rr, dd = G[lane], r[lane], d[lane]
-                u = k - dd
-                if s[lane] == 0:
-                    inp = X[k % RX, g * CH:(g + 1) * CH]
+                g, r = divmod(lane, NR)
+                isband = r < bpo
+                d = 0 if isband else r - bpo
+                isdec2 = (r == NR - 1)
+                maxstage = n_oct - 1 if isband else n_oct - 2
+                u = k - d
+                if d == 0:
+                    inp = X[k % RX, g * CH:(g + 1) * CH].copy()
                 else:
-                    inp = L[lane - 1, (k - 1) & 1]
+                    inp = L[lane - 1, (k - 1) & 1].copy()
                 out = np.full(CH, np.nan)
-                # segments: (slot_start, length, stage, chunk index, valid)
+                cA, n1A, n2A, cB, n1B, n2B = sec_coefs(r)
                 segs = []
-                for gg in range(logch):            # len CH/2 ... 1
+                for gg in range(logch):
                     ln = CH >> (gg + 1)
                     st = CH - 2 * ln
                     stage = g * (gg + 1)
                     cidx = u - (T[stage] if g else 0)
-                    valid = (0 <= cidx < n_chunks) and stage <= maxstage[lane]
+                    valid = (0 <= cidx < n_chunks) and stage <= maxstage
                     segs.append((st, ln, stage, cidx, valid))
-                # ruler slot
                 if g == 0:
-                    segs.append((CH - 1, 1, 0, u, (0 <= u < n_chunks) and 0 <= maxstage[lane]))
-                    jr, m = 0, u
+                    segs.append((CH - 1, 1, 0, u, (0 <= u < n_chunks) and 0 <= maxstage))
                 else:
                     jr = JR + ctz(u + 1) if u >= 0 else 99
-                    valid = False
-                    m = -1
-                    if jr <= maxstage[lane] and u >= T[jr]:
+                    valid, m = False, -1
+                    if jr <= maxstage and u >= T[jr]:
                         m = (u - T[jr]) >> (jr - logch)
                         valid = m < (t_total >> jr)
                     segs.append((CH - 1, 1, min(jr, MAX_OCT - 1), m, valid))
+                    if d == 0:
+                        inp[CH - 1] = MB[min(jr, MAX_OCT), m & 1] if valid else np.nan
                 for (st, ln, stage, cidx, valid) in segs:
-                    z1, z2, e = S[stage, rr]
+                    z1a, z2a, z1b, z2b = S[stage, r]
                     for i in range(st, st + ln):
                         xv = inp[i]
-                        y = xv + z1
-                        z1 = na1[lane] * y + (cc[lane] * xv + z2)
-                        z2 = na2[lane] * y + xv
-                        out[i] = y
-                    if st == CH - 1 and g == 1 and isband[lane] and s[lane] == 1:
-                        # ruler stage smoothing in the lane (e/alpha form)
-                        b = rr // 2
-                        yy = out[CH - 1] * self.g_band[b]
-                        e = e * self.q[stage] + yy * yy
-                        if valid and ((cidx + 1) & ((block >> stage) - 1)) == 0:
-                            kb, val = band_out(stage, b, e)
-                            energies[(cidx + 1) // (block >> stage) - 1, kb] = val
+                        ya = xv + z1a
+                        z1a = n1A * ya + (cA * xv + z2a)
+                        z2a = n2A * ya + xv
+                        yb = ya + z1b
+                        z1b = n1B * yb + (cB * ya + z2b)
+                        z2b = n2B * yb + ya
+                        out[i] = yb
                     if valid:
-                        S[stage, rr] = (z1, z2, e)
-                if isdec5[lane]:
+                        S[stage, r] = (z1a, z2a, z1b, z2b)
+                    if st == CH - 1 and g == 1 and isband:
+                        yy = out[CH - 1] * self.g_band[r]
+                        e = ER[stage, r] * self.q[stage] + yy * yy
+                        if valid:
+                            ER[stage, r] = e
+                            if ((cidx + 1) & ((block >> stage) - 1)) == 0:
+                                kb, val = band_out(stage, r, e)
+                                energies[(cidx + 1) // (block >> stage) - 1, kb] = val
+                if isband:
+                    BOw[(g, r)] = out
+                elif isdec2:
                     base = CH + g * (CH // 2)
-                    for i in range(0, CH - 4, 2):
+                    for i in range(0, CH - 2, 2):
                         Xw[((k + 1) % RX, base + i // 2)] = out[i] * self.g_dec
-                    Xw[((k + 1) % RX, base + (CH - 4) // 2)] = out[CH - 4] * self.g_dec
                     if g == 0:
                         Xw[((k + 1) % RX, base + (CH - 2) // 2)] = out[CH - 2] * self.g_dec
                     else:
-                        st, ln, stage, cidx, valid = segs[logch - 1]     # the len-1 stage JR-1
+                        st, ln, stage, cidx, valid = segs[logch - 1]     # the 1-sample stage JR-1
                         if valid and (cidx % 2 == 0):
-                            MBw[JR] = out[CH - 2] * self.g_dec
+                            MBw[(JR, (cidx // 2) & 1)] = out[CH - 2] * self.g_dec
                         st, ln, stage, cidx, valid = segs[logch]
                         if valid and (cidx % 2 == 0):
-                            MBw[stage + 1] = out[CH - 1] * self.g_dec
+                            MBw[(stage + 1, (cidx // 2) & 1)] = out[CH - 1] * self.g_dec
                 else:
                     Lnew[lane] = out
             for lane, out in Lnew.items():
                 L[lane, k & 1] = out
+            for (g, r), out in BOw.items():
+                BO[g, r] = out
             for (slot, pos), v in Xw.items():
                 X[slot, pos] = v
-            for j, v in MBw.items():
-                MB[j] = v
+            for (j, par), v in MBw.items():
+                MB[j, par] = v
             # ---------------------------------------------------------------- phase B
-            c0 = k - 1
+            c0 = k
             valid0 = 0 <= c0 < n_chunks
             for b in range(bpo):
-                y0 = L[2 * b + 1, k & 1] * self.g_band[b]
-                ym = L[NSEC + 2 * b + 1, k & 1] * self.g_band[b]
+                y0 = BO[0, b] * self.g_band[b]
+                ym = BO[1, b] * self.g_band[b]
                 if valid0:
                     acc0[b] = acc0[b] * Q0 + y0 * y0
                     if ((c0 + 1) & (NB - 1)) == 0:
@@ -250,7 +248,7 @@ class PipeModel:
                         acc0[b] = 0.0
                         acc0[b, CH - 1] = tot
                 for j in range(1, min(JR, n_oct)):
-                    cm = k - 1 - T[j]
+                    cm = k - T[j]
                     if not (0 <= cm < n_chunks):
                         continue
                     lo, hi = CH - 2 * len_of(j), CH - len_of(j)
@@ -261,20 +259,15 @@ class PipeModel:
                         energies[(cm + 1) // NB - 1, kb] = val
                         accm[b, lo:hi] = 0.0
                         accm[b, hi - 1] = tot
-            # prefetch chunk k + PF, mailbox -> X for the next step
             cn = k + PF
             if cn < n_chunks:
                 X[cn % RX, :CH] = x[cn * CH:(cn + 1) * CH]
-            jn = JR + ctz(k + 2)
-            if jn <= n_oct - 1:
-                X[(k + 1) % RX, 2 * CH - 1] = MB[jn]
         # epilogue: canonical state
-        self.z = S[:n_oct, :, :2].copy()
+        self.z = S[:n_oct].reshape(n_oct, self.NSEC, 2).copy()
         self.e[0] = acc0[:, CH - 1]
         for j in range(1, min(JR, n_oct)):
             self.e[j] = accm[:, CH - len_of(j) - 1]
         for j in range(JR, n_oct):
-            for b in range(bpo):
-                self.e[j, b] = S[j, 2 * b + 1, 2]
+            self.e[j] = ER[j]
         assert not np.isnan(energies).any(), "some band energies were never emitted"
         return energies
