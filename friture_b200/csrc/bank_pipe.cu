@@ -118,20 +118,40 @@ __device__ __forceinline__ float lg2_fast(float v) {
     return r;
 }
 
+// what the energy writers need, by value (taking the address of the kernel parameter would move it
+// to local memory)
+struct EmitCtx {
+    float *base;           // energies of this half-warp's first channel, or NULL
+    const float *weight;   // dB offsets or NULL
+    long long ch_stride;   // floats between consecutive channels (n_blocks * nbands)
+    int nbands;
+    int db;
+    int has2;
+};
+
 // friture/octavespectrum.py:119-121: 10*log10(sp + 1e-30) + w
-__device__ __forceinline__ float energy_out(float e, int kband, const BankArgs &a) {
-    if (!a.db) return e;
+__device__ __forceinline__ float energy_out(float e, int kband, const EmitCtx &c) {
+    if (!c.db) return e;
     float v = 3.01029995663981195f * lg2_fast(e + 1e-30f);
-    if (a.weight) v += __ldg(a.weight + kband);
+    if (c.weight) v += __ldg(c.weight + kband);
     return v;
 }
 
 template <class T>
-__device__ __noinline__ void emit(const BankArgs &a, float alpha_j, T val, int ch0, bool has2,
-                                  int blk, int kband, int nbands) {
-    float *o = a.energies + ((size_t)ch0 * a.n_blocks + blk) * nbands + kband;
-    o[0] = energy_out(alpha_j * v_x(val), kband, a);
-    if (sizeof(T) == 8 && has2) o[(size_t)a.n_blocks * nbands] = energy_out(alpha_j * v_y(val), kband, a);
+__device__ __noinline__ void emit(EmitCtx c, float alpha_j, T val, int blk, int kband) {
+    float *o = c.base + (size_t)blk * c.nbands + kband;
+    o[0] = energy_out(alpha_j * v_x(val), kband, c);
+    if (sizeof(T) == 8 && c.has2) o[c.ch_stride] = energy_out(alpha_j * v_y(val), kband, c);
+}
+
+// The two lane groups of a half-warp must run ONE instruction stream with per-lane predicates.
+// Conditions on the (loop-invariant) group index invite the compiler to unswitch the whole
+// section loop into two divergent copies, which doubles the issue slots; passing the flag through
+// an empty asm makes every use a fresh value.
+__device__ __forceinline__ bool opq(bool p) {
+    int v = p ? 1 : 0;
+    asm volatile("" : "+r"(v));
+    return v != 0;
 }
 
 // normalised biquad step (bank_internal.cuh): y = x + z1; z1 = c x - a1 y + z2; z2 = x - a2 y
@@ -155,21 +175,33 @@ __host__ __device__ constexpr bool seg_starts_at(int slot, int ch) {
     return slot >= ch / 2 && ((ch - slot) & (ch - slot - 1)) == 0;
 }
 
+// Shared memory of one channel slot (half-warp), in units of T.  128-bit accesses are served a
+// quarter-warp (8 lanes x 16 B) at a time, so the 8 lanes of a quarter must hit 8 different 16-byte
+// bank groups: every writer lane hl owns a region whose base is 16*hl (mod 128) bytes, the stage
+// input vectors sit in groups 5 (stage 0) and 6 (multiplexed stages), and the second half-warp's
+// slot is displaced by 64 (mod 128) bytes so that the 32-bit accesses of the two halves use
+// different banks.
 template <int LOGCH, int PACK, int BPO>
-struct PipeLayout {     // shared memory of one channel slot (half-warp), in units of T
+struct PipeLayout {
     static constexpr int CH = 1 << LOGCH;
     static constexpr int NR = BPO + DEC_DEPTH;
     static constexpr int TB = 4 * PACK;                       // bytes per T
-    static constexpr int PAD = 16 / TB;                       // 16 B of bank skew between buffers
-    static constexpr int X = 0;                               // [RX][2 CH]
-    static constexpr int L = X + PIPE_RX * 2 * CH;            // [2 groups][2 links][2 bufs][CH + PAD]
-    static constexpr int LBUF = CH + PAD;
-    static constexpr int BO = L + 8 * LBUF;                   // [2 groups][BPO][CH + PAD]
-    static constexpr int S = BO + 2 * BPO * LBUF;             // [MAX_OCT][NR][4]: z1A z2A z1B z2B
+    static constexpr int PAD = 16 / TB;                       // 16 bytes
+    static constexpr int XSLOT = 2 * CH + 8 * PAD;            // ring slot: 128 B of skew + 2 vectors
+    static constexpr int X0 = 5 * PAD;                        // stage-0 chunk within a slot (group 5)
+    static constexpr int XM = X0 + CH + PAD;                  // multiplexed vector (group 6)
+    static constexpr int X = 0;                               // [RX][XSLOT]
+    static constexpr int W = X + PIPE_RX * XSLOT;             // [12 writer lanes][2 bufs][CH] + 16 B each
+    static constexpr int WSTR = 2 * CH + PAD;
+    static constexpr int S = W + 12 * WSTR + 4 * PAD;         // [MAX_OCT][NR][4]: z1A z2A z1B z2B
     static constexpr int ER = S + BANK_MAX_OCT * NR * 4;      // [MAX_OCT][4]: ruler-stage energies
     static constexpr int MB = ER + BANK_MAX_OCT * 4;          // [MAX_OCT + 2][2] mailboxes
-    static constexpr int TOTAL = MB + (BANK_MAX_OCT + 2) * 2;
-    static_assert(TOTAL % PAD == 0 || PAD == 1, "16-byte multiple");
+    static constexpr int RAW = MB + (BANK_MAX_OCT + 2) * 2;
+    // round up to 64 (mod 128) bytes
+    static constexpr int RAWB = RAW * TB;
+    static constexpr int TOTALB = ((RAWB + 63) / 128) * 128 + 64;
+    static constexpr int TOTAL = TOTALB / TB;
+    static_assert((12 * WSTR + 4 * PAD) % (8 * PAD) == 0, "state rows start on a 128-byte boundary");
 };
 
 template <int LOGCH, int PACK, int BPO>
@@ -186,14 +218,13 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
     static_assert(LOGCH == 5 || LOGCH == 6, "steps of 32 or 64 samples");
     static_assert(NG % GB == 0, "whole load batches");
 
-    extern __shared__ float4 smem4[];
+    extern __shared__ __align__(128) float4 smem4[];
     const int lane = threadIdx.x;
     const int h = lane >> 4, hl = lane & 15;
     T *sm = reinterpret_cast<T *>(smem4) + h * LY::TOTAL;       // this half-warp's channel slot
     int *sT = reinterpret_cast<int *>(reinterpret_cast<T *>(smem4) + 2 * LY::TOTAL);   // [MAX_OCT + 2]
     float *sAl = reinterpret_cast<float *>(sT + 12);            // [MAX_OCT + 2]
-    T *sX = sm + LY::X, *sL = sm + LY::L, *sBO = sm + LY::BO, *sS = sm + LY::S, *sER = sm + LY::ER,
-      *sMB = sm + LY::MB;
+    T *sX = sm + LY::X, *sW = sm + LY::W, *sS = sm + LY::S, *sER = sm + LY::ER, *sMB = sm + LY::MB;
 
     // channels of this half-warp (clamped when the last warp is not full; `alive` gates the writes)
     const int cgrp = blockIdx.x * 2 + h;
@@ -208,6 +239,13 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
     const int nbmask = (1 << lognb) - 1;
     const int logblock = lognb + LOGCH;
     const bool want_e = alive && a.energies != nullptr;
+    EmitCtx ectx;
+    ectx.base = a.energies ? a.energies + (size_t)ch0 * a.n_blocks * nbands : nullptr;
+    ectx.weight = a.db ? a.weight : nullptr;
+    ectx.ch_stride = (long long)a.n_blocks * nbands;
+    ectx.nbands = nbands;
+    ectx.db = a.db;
+    ectx.has2 = has2 ? 1 : 0;
 
     // ---- lane roles (phase A)
     const bool worker = hl < 2 * NR;
@@ -273,7 +311,7 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
     const bool vec16 = (PACK == 1) && a.vec_ok;
     auto prefetch = [&](int cn) {
         if (cn < n_chunks) {
-            T *dst = sX + (cn & (RX - 1)) * 2 * CH;
+            T *dst = sX + (cn & (RX - 1)) * LY::XSLOT + LY::X0;
             if (vec16) {
                 if (hl < CH / 4) cp_async16(dst + 4 * hl, x0 + (size_t)cn * CH + 4 * hl);
             } else {
@@ -307,11 +345,12 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
     auto phaseA = [&](int k, auto check_tag) {
         constexpr bool CHECK = decltype(check_tag)::value;
         const int u = k - d;
-        const T *inp = ishead ? sX + (k & (RX - 1)) * 2 * CH + G * CH
-                              : sL + ((G * 2 + d - 1) * 2 + ((k - 1) & 1)) * LY::LBUF;
-        T *outp = isband ? sBO + (G * BPO + r) * LY::LBUF
-                         : sL + ((G * 2 + d) * 2 + (k & 1)) * LY::LBUF;
-        T *xn = sX + ((k + 1) & (RX - 1)) * 2 * CH + CH + G * (CH / 2);
+        // heads read the stage input vector, the other decimator lanes the buffer their predecessor
+        // (lane hl-1) filled one step earlier; every lane writes its own region (buffer k&1)
+        const T *inp = ishead ? sX + (k & (RX - 1)) * LY::XSLOT + (G ? LY::XM : LY::X0)
+                              : sW + (hl - 1) * LY::WSTR + ((k - 1) & 1) * CH;
+        T *outp = sW + hl * LY::WSTR + (k & 1) * CH;
+        T *xn = sX + ((k + 1) & (RX - 1)) * LY::XSLOT + LY::XM + G * (CH / 2);
         const bool pv0 = !CHECK || ((unsigned)u < (unsigned)n_chunks && 0 <= maxstage);
         // ruler slot: the stage >= JR whose sample is due (group 1 only)
         const int jr = JR - 1 + __ffs(u + 1);
@@ -321,20 +360,17 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
         bool pvR = jr <= maxstage;
         if (CHECK) pvR = pvR && u >= Tj && m < (int)(a.t_total >> jrc);
 
-        // section state: group 0 keeps it in registers (zc); group 1 switches rows of sS at every
-        // segment start, the next row is fetched one segment ahead
+        // section state: group 0 keeps it in registers (zc) for the whole step; group 1 switches
+        // rows of sS at every segment start, the next row is fetched one segment ahead.  Loads are
+        // unconditional (group 0 reads rows it never uses), selection is by per-lane predicate.
+        const bool g1 = opq(G != 0);
         T cur[4], nxt[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) cur[i] = zc[i];
         T *spc = sS + (1 * NR + r) * 4;        // state row of the segment being processed (group 1)
-        bool pvc = pv0;
-        if (G) {
 #pragma unroll
-            for (int i = 0; i < 4; i++) cur[i] = spc[i];
+        for (int i = 0; i < 4; i++) cur[i] = v_sel(g1, spc[i], zc[i]);
 #pragma unroll
-            for (int i = 0; i < 4; i++) nxt[i] = sS[(2 * NR + r) * 4 + i];
-            pvc = !CHECK || ((unsigned)(u - DEC_DEPTH) < (unsigned)n_chunks && 1 <= maxstage);
-        }
+        for (int i = 0; i < 4; i++) nxt[i] = sS[(2 * NR + r) * 4 + i];
+        bool pvc = !CHECK || ((unsigned)(u - DEC_DEPTH) < (unsigned)n_chunks && 1 <= maxstage);
         bool pvB = false;           // validity / chunk index of the 1-sample stage LOGCH (for the mailbox)
         int cidxB = 0;
 #pragma unroll
@@ -344,7 +380,8 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
             for (int q = 0; q < GB; q++) ld4(inp + 4 * (b0 + q), v[q]);
             if (b0 + GB == NG) {
                 // the ruler stage's sample comes from its mailbox, not from the ring
-                if (G && ishead) v[GB - 1][3] = sMB[jrc * 2 + (m & 1)];
+                const T mb = sMB[jrc * 2 + (m & 1)];
+                v[GB - 1][3] = v_sel(opq(G != 0 && ishead), mb, v[GB - 1][3]);
             }
 #pragma unroll
             for (int q = 0; q < GB; q++) {
@@ -355,28 +392,27 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
                     if (seg_starts_at(slot, CH)) {
                         // group 1 switches to the state of the next stage; group 0 keeps its registers
                         const int g = LOGCH - ilog2c(CH - slot);
-                        if (G) {
-                            if (pvc) {
+                        const bool gs = opq(G != 0);
+                        if (gs && pvc) {
 #pragma unroll
-                                for (int e = 0; e < 4; e++) spc[e] = cur[e];
+                            for (int e = 0; e < 4; e++) spc[e] = cur[e];
+                        }
+#pragma unroll
+                        for (int e = 0; e < 4; e++) cur[e] = v_sel(gs, nxt[e], cur[e]);
+                        spc = (g < LOGCH) ? sS + ((g + 1) * NR + r) * 4 : sS + (jrc * NR + r) * 4;
+                        if (g < LOGCH) {
+                            const T *spn = (g + 1 < LOGCH) ? sS + ((g + 2) * NR + r) * 4
+                                                           : sS + (jrc * NR + r) * 4;
+#pragma unroll
+                            for (int e = 0; e < 4; e++) nxt[e] = spn[e];
+                            pvc = !CHECK || ((unsigned)(u - DEC_DEPTH * (g + 1)) < (unsigned)n_chunks &&
+                                             (g + 1) <= maxstage);
+                            if (g == LOGCH - 1) {
+                                pvB = pvc;
+                                cidxB = u - DEC_DEPTH * (g + 1);
                             }
-#pragma unroll
-                            for (int e = 0; e < 4; e++) cur[e] = nxt[e];
-                            spc = (g < LOGCH) ? sS + ((g + 1) * NR + r) * 4 : sS + (jrc * NR + r) * 4;
-                            if (g < LOGCH) {
-                                const T *spn = (g + 1 < LOGCH) ? sS + ((g + 2) * NR + r) * 4
-                                                               : sS + (jrc * NR + r) * 4;
-#pragma unroll
-                                for (int e = 0; e < 4; e++) nxt[e] = spn[e];
-                                pvc = !CHECK || ((unsigned)(u - DEC_DEPTH * (g + 1)) < (unsigned)n_chunks &&
-                                                 (g + 1) <= maxstage);
-                                if (g == LOGCH - 1) {
-                                    pvB = pvc;
-                                    cidxB = u - DEC_DEPTH * (g + 1);
-                                }
-                            } else {
-                                pvc = pvR;
-                            }
+                        } else {
+                            pvc = pvR;
                         }
                     }
                     const T ya = biquad(v[q][i], cur[0], cur[1], cA, n1A, n2A);
@@ -388,18 +424,16 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
                     else st2(xn + 2 * gq, v_mul(gdec, y[0]), v_mul(gdec, y[2]));
                 } else {
                     // last group: slots CH-4, CH-3 (a 2-sample stage), CH-2 (a 1-sample stage), CH-1 (ruler)
+                    const bool gl = opq(G != 0);
                     if (!isdec2) {
                         st4(outp + 4 * gq, y);
                     } else {
                         xn[2 * gq] = v_mul(gdec, y[0]);
-                        if (!G) {
-                            xn[2 * gq + 1] = v_mul(gdec, y[2]);
-                        } else {
-                            if (pvB && !(cidxB & 1)) sMB[JR * 2 + ((cidxB >> 1) & 1)] = v_mul(gdec, y[2]);
-                            if (pvR && !(m & 1)) sMB[(jrc + 1) * 2 + ((m >> 1) & 1)] = v_mul(gdec, y[3]);
-                        }
+                        if (!gl) xn[2 * gq + 1] = v_mul(gdec, y[2]);
+                        if (gl && pvB && !(cidxB & 1)) sMB[JR * 2 + ((cidxB >> 1) & 1)] = v_mul(gdec, y[2]);
+                        if (gl && pvR && !(m & 1)) sMB[(jrc + 1) * 2 + ((m >> 1) & 1)] = v_mul(gdec, y[3]);
                     }
-                    if (G && isband) {
+                    if (gl && isband) {
                         // exp_smoothed_value of the low-rate stages: e <- (1-alpha) e + y^2 (e/alpha form)
                         const float alj = sAl[jrc];
                         T e = sER[jrc * 4 + r];
@@ -409,22 +443,19 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
                             sER[jrc * 4 + r] = e;
                             const int bl = logblock - jrc;           // block >> jrc = 2^bl samples
                             if (want_e && ((m + 1) & ((1 << bl) - 1)) == 0)
-                                emit<T>(a, alj, e, ch0, has2, ((m + 1) >> bl) - 1,
-                                        (n_oct - 1 - jrc) * BPO + r, nbands);
+                                emit<T>(ectx, alj, e, ((m + 1) >> bl) - 1, (n_oct - 1 - jrc) * BPO + r);
                         }
                     }
                 }
             }
         }
-        if (G) {
-            if (pvc) {
+        const bool ge = opq(G != 0);
+        if (ge && pvc) {
 #pragma unroll
-                for (int e = 0; e < 4; e++) spc[e] = cur[e];
-            }
-        } else if (pv0) {
-#pragma unroll
-            for (int e = 0; e < 4; e++) zc[e] = cur[e];
+            for (int e = 0; e < 4; e++) spc[e] = cur[e];
         }
+#pragma unroll
+        for (int e = 0; e < 4; e++) zc[e] = v_sel(!ge && pv0, cur[e], zc[e]);
     };
 
     // ================================================================ phase B: smoothing, prefetch
@@ -439,8 +470,8 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
         }
 #pragma unroll
         for (int b = 0; b < BPO; b++) {
-            const T *y0p = sBO + b * LY::LBUF;
-            const T *ymp = sBO + (BPO + b) * LY::LBUF;
+            const T *y0p = sW + b * LY::WSTR + (k & 1) * CH;            // band b of group 0 / group 1
+            const T *ymp = sW + (NR + b) * LY::WSTR + (k & 1) * CH;
             const float gb = P.gband[b];
 #pragma unroll
             for (int q = 0; q < NSL; q++) {
@@ -466,7 +497,7 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
                     v_set(acc0[b][q], 0.f, 0.f);
                     if (hl + 16 * q == CH - 1) acc0[b][q] = val;
                 }
-                if (hl == 0 && want_e) emit<T>(a, P.alpha[0], val, ch0, has2, blk, (n_oct - 1) * BPO + b, nbands);
+                if (hl == 0 && want_e) emit<T>(ectx, P.alpha[0], val, blk, (n_oct - 1) * BPO + b);
             }
         }
 #pragma unroll
@@ -493,7 +524,7 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
                         v_set(accm[b][q], 0.f, 0.f);
                         if (hl + 16 * q == lo + len - 1) accm[b][q] = val;
                     }
-                    if (hl == 0 && want_e) emit<T>(a, sAl[j], val, ch0, has2, blk, kb0 + b, nbands);
+                    if (hl == 0 && want_e) emit<T>(ectx, sAl[j], val, blk, kb0 + b);
                 }
             } else {
                 // the stage sits in lanes [lo & 15, (lo & 15) + len) of the last register
@@ -512,7 +543,7 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
                     if (mine) {
                         v_set(accm[b][q], 0.f, 0.f);
                         if (hl == l0 + len - 1) accm[b][q] = val;
-                        if (hl == l0 && want_e) emit<T>(a, sAl[j], val, ch0, has2, blk, kb0 + b, nbands);
+                        if (hl == l0 && want_e) emit<T>(ectx, sAl[j], val, blk, kb0 + b);
                     }
                 }
             }
