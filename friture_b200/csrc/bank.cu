@@ -145,15 +145,14 @@ __device__ __forceinline__ void bands_of_stage(const float (&xc)[L], const W &w,
         section_scan<L>(wk, wk, w, j, 2 * i + 1);
         const int kband = (P.n_oct - 1 - j) * bpo + i;
         const float gb = P.gband[i];     // chain gain of the normalised sections
-#pragma unroll
-        for (int k = 0; k < L; k++) wk[k] *= gb;
         if constexpr (W::kWantY) {
             float *yp = w.y + y_offset(kband, bpo, P.n_oct, w.t_total) + (w.t_off >> j) +
                         w.lane * L;
 #pragma unroll
-            for (int k = 0; k < L; k++) yp[k] = wk[k];
+            for (int k = 0; k < L; k++) yp[k] = wk[k] * gb;
         }
-        // exponential smoothing of y^2 (friture/signal/exp_smoothing.py:11-56), e/alpha form;
+        // exponential smoothing of y^2 (friture/signal/exp_smoothing.py:11-56), e/alpha form, in the
+        // units of the normalised sections (the squared chain gain is applied to the output);
         // decays in complement form e - (1-q^n) e: the rounding of q must not bias long time constants
         const float om = P.omq[j][0];
         float e = 0.f;
@@ -170,7 +169,7 @@ __device__ __forceinline__ void bands_of_stage(const float (&xc)[L], const W &w,
         __syncwarp();
         if (w.lane == 31) {
             ep[0] = e;
-            if (w.energies) w.energies[kband] = energy_out(P.alpha[j] * e, w.db, w.weight, kband);
+            if (w.energies) w.energies[kband] = energy_out(P.alpha[j] * gb * gb * e, w.db, w.weight, kband);
         }
     }
 }
@@ -292,12 +291,13 @@ __device__ __forceinline__ void serial_stages(float xin, int n, const W &w, int 
                     v = y;
                 }
             }
-            v *= gout;
             if (is_band) {
-                e = fmaf(-om, e, e) + v * v;
+                e = fmaf(-om, e, e) + v * v;      // raw units; gain applied to the outputs
                 if constexpr (W::kWantY) {
-                    if (yp) yp[m] = v;
+                    if (yp) yp[m] = v * gout;
                 }
+            } else {
+                v *= gout;
             }
             if ((m & 1) == 0) {   // keep even samples (friture/signal/decimate.py:41)
                 const float o = __shfl_sync(0xffffffffu, v, bpo);
@@ -315,7 +315,7 @@ __device__ __forceinline__ void serial_stages(float xin, int n, const W &w, int 
         }
         if (is_band) {
             w.s_e[j * bpo + lane] = e;
-            if (w.energies) w.energies[kband] = energy_out(P.alpha[j] * e, w.db, w.weight, kband);
+            if (w.energies) w.energies[kband] = energy_out(P.alpha[j] * gout * gout * e, w.db, w.weight, kband);
         }
         __syncwarp();
         xin = xnext;
