@@ -176,7 +176,8 @@ struct PipeLayout {
     static constexpr int ER = SR + BANK_MAX_OCT * NR * 4;     // [MAX_OCT][4]: ruler-stage energies
     static constexpr int MB = ER + BANK_MAX_OCT * 4;          // [MAX_OCT + 2][2] mailboxes
     static constexpr int EN = MB + (BANK_MAX_OCT + 2) * 2;    // [EN_RING][32] staged band energies
-    static constexpr int RAW = EN + EN_RING * 32;
+    static constexpr int ACC = EN + EN_RING * 32;             // [2 vectors][BPO][CH] smoothing accumulators
+    static constexpr int RAW = ACC + 2 * BPO * CH;
     // channel stride = NR*16 (mod 128) bytes
     static constexpr int RAWB = RAW * TB;
     static constexpr int WANT = (NR * 16) % 128;
@@ -304,26 +305,26 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
                                       : sW + (r - 1) * LY::WSTR + ((k - 1) & 1) * CH;
                 T *outp = sW + r * LY::WSTR + (k & 1) * CH;
                 T *xn = sX + ((k + 1) & (RX - 1)) * LY::XSLOT + LY::XM;
-                T cur[4];
+                T cur[4], vn[4];
 #pragma unroll
                 for (int i = 0; i < 4; i++) cur[i] = zc[i];
+                ld4(inp, vn);
+                // a rolled loop over the 4-sample groups keeps the hot code in the instruction cache;
+                // the next group's input is fetched while this one is computed
+#pragma unroll 1
+                for (int gq = 0; gq < NG; gq++) {
+                    T v[4], y[4];
 #pragma unroll
-                for (int b0 = 0; b0 < NG; b0 += GB) {
-                    T v[GB][4];
+                    for (int i = 0; i < 4; i++) v[i] = vn[i];
+                    ld4(inp + 4 * ((gq + 1) & (NG - 1)), vn);
 #pragma unroll
-                    for (int q = 0; q < GB; q++) ld4(inp + 4 * (b0 + q), v[q]);
-#pragma unroll
-                    for (int q = 0; q < GB; q++) {
-                        T y[4];
-#pragma unroll
-                        for (int i = 0; i < 4; i++) {
-                            const T ya = biquad(v[q][i], cur[0], cur[1], cA, n1A, n2A);
-                            y[i] = biquad(ya, cur[2], cur[3], cB, n1B, n2B);
-                        }
-                        // the last decimator lane keeps the even samples (friture/signal/decimate.py:41)
-                        if (!isdec2) st4(outp + 4 * (b0 + q), y);
-                        else st2(xn + 2 * (b0 + q), v_mul(gdec, y[0]), v_mul(gdec, y[2]));
+                    for (int i = 0; i < 4; i++) {
+                        const T ya = biquad(v[i], cur[0], cur[1], cA, n1A, n2A);
+                        y[i] = biquad(ya, cur[2], cur[3], cB, n1B, n2B);
                     }
+                    // the last decimator lane keeps the even samples (friture/signal/decimate.py:41)
+                    if (!isdec2) st4(outp + 4 * gq, y);
+                    else st2(xn + 2 * gq, v_mul(gdec, y[0]), v_mul(gdec, y[2]));
                 }
 #pragma unroll
                 for (int i = 0; i < 4; i++) zc[i] = v_sel(pv0, cur[i], zc[i]);
@@ -341,137 +342,124 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
         // ============================================================ stages >= 1, time-multiplexed
         const int maxstage = isband ? n_oct - 1 : n_oct - 2;
         const float gb2 = isband ? P.gband[r] * P.gband[r] : 0.f;
-        // section state of the chunked stages 1..LOGCH lives in registers
-        T st[LOGCH][4];
-#pragma unroll
-        for (int g = 0; g < LOGCH; g++) {
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                v_set(st[g][i], 0.f, 0.f);
-                if (g + 1 < n_oct) v_set(st[g][i], gz0[((g + 1) * NR + r) * 4 + i], gz1[((g + 1) * NR + r) * 4 + i]);
-            }
-        }
-        // steps in [k_lo, k_hi) have every slot of every lane valid: they skip the range checks
-        const int k_lo = P.T[n_oct - 1] + DEC_DEPTH;
-        const int k_hi = (n_oct > JR) ? n_chunks : 0;
-
-        auto step = [&](int k, auto check_tag) {
-            constexpr bool CHECK = decltype(check_tag)::value;
-            const int u = k - d;
-            const T *inp = ishead ? sX + (k & (RX - 1)) * LY::XSLOT + LY::XM
-                                  : sW + (NR + r - 1) * LY::WSTR + ((k - 1) & 1) * CH;
-            T *outp = sW + (NR + r) * LY::WSTR + (k & 1) * CH;
-            T *xn = sX + ((k + 1) & (RX - 1)) * LY::XSLOT + LY::XM + CH / 2;
-            // ruler slot: the stage >= JR whose sample is due
-            const int jr = JR - 1 + __ffs(u + 1);
-            const int jrc = jr < BANK_MAX_OCT - 1 ? jr : BANK_MAX_OCT - 1;
-            const int Tj = sT[jrc];
-            const int m = (u - Tj) >> (jrc - LOGCH);
-            bool pvR = jr <= maxstage;
-            if (CHECK) pvR = pvR && u >= Tj && m < (int)(a.t_total >> jrc);
-            T *spr = sSR + (jrc * NR + r) * 4;
-            T zr[4];
-#pragma unroll
-            for (int i = 0; i < 4; i++) zr[i] = spr[i];
-            const T mb = sMB[jrc * 2 + (m & 1)];
-            bool pvB = true;        // validity / chunk index of the 1-sample stage LOGCH (for the mailbox)
-            const int cidxB = u - DEC_DEPTH * LOGCH;
-            T ylast[4];
-#pragma unroll
-            for (int b0 = 0; b0 < NG; b0 += GB) {
-                T v[GB][4];
-#pragma unroll
-                for (int q = 0; q < GB; q++) ld4(inp + 4 * (b0 + q), v[q]);
-                if (b0 + GB == NG)     // the ruler stage's sample comes from its mailbox, not from the ring
-                    v[GB - 1][3] = v_sel(ishead, mb, v[GB - 1][3]);
-#pragma unroll
-                for (int q = 0; q < GB; q++) {
-                    T y[4];
-#pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        const int slot = 4 * (b0 + q) + i;
-                        const int g = seg_of_slot(slot, CH, LOGCH);
-                        if (g < LOGCH) {
-                            T s0 = st[g][0], s1 = st[g][1], s2 = st[g][2], s3 = st[g][3];
-                            const T ya = biquad(v[q][i], s0, s1, cA, n1A, n2A);
-                            y[i] = biquad(ya, s2, s3, cB, n1B, n2B);
-                            bool pv = true;
-                            if (CHECK) pv = (unsigned)(u - DEC_DEPTH * (g + 1)) < (unsigned)n_chunks && (g + 1) <= maxstage;
-                            if (CHECK) {
-                                st[g][0] = v_sel(pv, s0, st[g][0]); st[g][1] = v_sel(pv, s1, st[g][1]);
-                                st[g][2] = v_sel(pv, s2, st[g][2]); st[g][3] = v_sel(pv, s3, st[g][3]);
-                            } else {
-                                st[g][0] = s0; st[g][1] = s1; st[g][2] = s2; st[g][3] = s3;
-                            }
-                            if (g == LOGCH - 1) pvB = pv;
-                        } else {
-                            const T ya = biquad(v[q][i], zr[0], zr[1], cA, n1A, n2A);
-                            y[i] = biquad(ya, zr[2], zr[3], cB, n1B, n2B);
-                        }
-                    }
-                    const int gq = b0 + q;
-                    if (gq < NG - 1) {
-                        if (!isdec2) st4(outp + 4 * gq, y);
-                        else st2(xn + 2 * gq, v_mul(gdec, y[0]), v_mul(gdec, y[2]));
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 4; i++) ylast[i] = y[i];
-                    }
-                }
-            }
-            // last group: slots CH-4, CH-3 (a 2-sample stage), CH-2 (a 1-sample stage), CH-1 (ruler)
-            if (!isdec2) {
-                st4(outp + CH - 4, ylast);
-            } else {
-                xn[CH / 2 - 2] = v_mul(gdec, ylast[0]);
-                if (pvB && !(cidxB & 1)) sMB[JR * 2 + ((cidxB >> 1) & 1)] = v_mul(gdec, ylast[2]);
-                if (pvR && !(m & 1)) sMB[(jrc + 1) * 2 + ((m >> 1) & 1)] = v_mul(gdec, ylast[3]);
-            }
-            if (pvR) {
-#pragma unroll
-                for (int i = 0; i < 4; i++) spr[i] = zr[i];
-            }
-            if (isband) {
-                // exp_smoothed_value of the low-rate stages: e <- (1-alpha) e + y^2 (e/alpha form, raw units)
-                const float alj = sAl[jrc];
-                T e = sER[jrc * 4 + r];
-                e = v_add(v_fma(-alj, e, e), v_sq(ylast[3]));
-                if (pvR) {
-                    sER[jrc * 4 + r] = e;
-                    const int bl = logblock - jrc;           // block >> jrc = 2^bl samples
-                    if (((m + 1) & ((1 << bl) - 1)) == 0) {
-                        const int blk = ((m + 1) >> bl) - 1;
-                        sEN[(blk & (EN_RING - 1)) * 32 + (n_oct - 1 - jrc) * BPO + r] = v_mul(alj * gb2, e);
-                    }
-                }
-            }
-        };
         for (int k = 0; k < n_steps; k++) {
             if (worker) {
-                if (k >= k_lo && k < k_hi) step(k, std::false_type());
-                else step(k, std::true_type());
+                const int u = k - d;
+                const T *inp = ishead ? sX + (k & (RX - 1)) * LY::XSLOT + LY::XM
+                                      : sW + (NR + r - 1) * LY::WSTR + ((k - 1) & 1) * CH;
+                T *outp = sW + (NR + r) * LY::WSTR + (k & 1) * CH;
+                T *xn = sX + ((k + 1) & (RX - 1)) * LY::XSLOT + LY::XM + CH / 2;
+                // ruler slot: the stage >= JR whose sample is due
+                const int jr = JR - 1 + __ffs(u + 1);
+                const int jrc = jr < BANK_MAX_OCT - 1 ? jr : BANK_MAX_OCT - 1;
+                const int Tj = sT[jrc];
+                const int m = (u - Tj) >> (jrc - LOGCH);
+                const bool pvR = jr <= maxstage && u >= Tj && m < (int)(a.t_total >> jrc);
+                T *spr = sSR + (jrc * NR + r) * 4;
+                T zr[4];
+#pragma unroll
+                for (int i = 0; i < 4; i++) zr[i] = spr[i];
+                const T mb = sMB[jrc * 2 + (m & 1)];
+                // section state: one row of sSR per stage; the next row is fetched a segment ahead
+                T cur[4], nxt[4], vn[4];
+                T *spc = sSR + (1 * NR + r) * 4;
+#pragma unroll
+                for (int i = 0; i < 4; i++) cur[i] = spc[i];
+                bool pvc = (unsigned)(u - DEC_DEPTH) < (unsigned)n_chunks && 1 <= maxstage;
+                ld4(inp, vn);
+                int gq = 0;
+#pragma unroll 1
+                for (int g = 0; g <= LOGCH - 3; g++) {      // segments of 4+ samples: stage g+1, CH >> (g+1) slots
+                    T *spn = sSR + ((g + 2) * NR + r) * 4;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) nxt[i] = spn[i];
+                    const int ng = CH >> (g + 3);
+#pragma unroll 1
+                    for (int q = 0; q < ng; q++, gq++) {
+                        T v[4], y[4];
+#pragma unroll
+                        for (int i = 0; i < 4; i++) v[i] = vn[i];
+                        ld4(inp + 4 * (gq + 1), vn);
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            const T ya = biquad(v[i], cur[0], cur[1], cA, n1A, n2A);
+                            y[i] = biquad(ya, cur[2], cur[3], cB, n1B, n2B);
+                        }
+                        if (!isdec2) st4(outp + 4 * gq, y);
+                        else st2(xn + 2 * gq, v_mul(gdec, y[0]), v_mul(gdec, y[2]));
+                    }
+                    if (pvc) {
+#pragma unroll
+                        for (int i = 0; i < 4; i++) spc[i] = cur[i];
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; i++) cur[i] = nxt[i];
+                    spc = spn;
+                    pvc = (unsigned)(u - DEC_DEPTH * (g + 2)) < (unsigned)n_chunks && (g + 2) <= maxstage;
+                }
+                // last group: slots CH-4, CH-3 (stage LOGCH-1, state in cur), CH-2 (stage LOGCH), CH-1 (ruler)
+                T y[4];
+                {
+                    T *spn = sSR + (LOGCH * NR + r) * 4;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) nxt[i] = spn[i];
+                    vn[3] = v_sel(ishead, mb, vn[3]);     // the ruler stage's sample comes from its mailbox
+                    T ya = biquad(vn[0], cur[0], cur[1], cA, n1A, n2A);
+                    y[0] = biquad(ya, cur[2], cur[3], cB, n1B, n2B);
+                    ya = biquad(vn[1], cur[0], cur[1], cA, n1A, n2A);
+                    y[1] = biquad(ya, cur[2], cur[3], cB, n1B, n2B);
+                    if (pvc) {
+#pragma unroll
+                        for (int i = 0; i < 4; i++) spc[i] = cur[i];
+                    }
+                    const int cidxB = u - DEC_DEPTH * LOGCH;
+                    const bool pvB = (unsigned)cidxB < (unsigned)n_chunks && LOGCH <= maxstage;
+                    ya = biquad(vn[2], nxt[0], nxt[1], cA, n1A, n2A);
+                    y[2] = biquad(ya, nxt[2], nxt[3], cB, n1B, n2B);
+                    if (pvB) {
+#pragma unroll
+                        for (int i = 0; i < 4; i++) spn[i] = nxt[i];
+                    }
+                    ya = biquad(vn[3], zr[0], zr[1], cA, n1A, n2A);
+                    y[3] = biquad(ya, zr[2], zr[3], cB, n1B, n2B);
+                    if (pvR) {
+#pragma unroll
+                        for (int i = 0; i < 4; i++) spr[i] = zr[i];
+                    }
+                    if (!isdec2) {
+                        st4(outp + CH - 4, y);
+                    } else {
+                        xn[CH / 2 - 2] = v_mul(gdec, y[0]);
+                        if (pvB && !(cidxB & 1)) sMB[JR * 2 + ((cidxB >> 1) & 1)] = v_mul(gdec, y[2]);
+                        if (pvR && !(m & 1)) sMB[(jrc + 1) * 2 + ((m >> 1) & 1)] = v_mul(gdec, y[3]);
+                    }
+                }
+                if (isband) {
+                    // exp_smoothed_value of the low-rate stages: e <- (1-alpha) e + y^2 (e/alpha form, raw units)
+                    const float alj = sAl[jrc];
+                    T e = sER[jrc * 4 + r];
+                    e = v_add(v_fma(-alj, e, e), v_sq(y[3]));
+                    if (pvR) {
+                        sER[jrc * 4 + r] = e;
+                        const int bl = logblock - jrc;           // block >> jrc = 2^bl samples
+                        if (((m + 1) & ((1 << bl) - 1)) == 0) {
+                            const int blk = ((m + 1) >> bl) - 1;
+                            sEN[(blk & (EN_RING - 1)) * 32 + (n_oct - 1 - jrc) * BPO + r] = v_mul(alj * gb2, e);
+                        }
+                    }
+                }
             }
             __syncthreads();
         }
         if (alive) {
-#pragma unroll
-            for (int g = 0; g < LOGCH; g++) {
-                if (g + 1 < n_oct) {
-#pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        gz0[((g + 1) * NR + r) * 4 + i] = v_x(st[g][i]);
-                        if (has2) gz1[((g + 1) * NR + r) * 4 + i] = v_y(st[g][i]);
-                    }
-                }
-            }
-            for (int j = JR; j < n_oct; j++) {
+            for (int j = 1; j < n_oct; j++) {
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
                     const T z = sSR[(j * NR + r) * 4 + i];
                     gz0[(j * NR + r) * 4 + i] = v_x(z);
                     if (has2) gz1[(j * NR + r) * 4 + i] = v_y(z);
                 }
-                if (isband) {
+                if (isband && j >= JR) {
                     const T e = sER[j * 4 + r];
                     a.ema[(size_t)ch0 * nbands + j * BPO + r] = v_x(e);
                     if (has2) a.ema[(size_t)ch1 * nbands + j * BPO + r] = v_y(e);
@@ -480,10 +468,10 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
         }
     } else {
         // ============================================================ smoothing, energies, input prefetch
-        // lane = sample slot (slot = lane + 32 q); one accumulator per slot, band, channel and vector
-        T acc0[NCH][BPO][NSL], accm[NCH][BPO][NSL];
-        int mst[NSL], gsz[NSL];
-        bool mok[NSL], lastslot[NSL], firstslot[NSL];
+        // lane = sample slot (slot = lane + 32 q); one accumulator per slot, band, channel and vector,
+        // kept in shared memory so that the channel loops can stay rolled
+        int mst[NSL];
+        bool mok[NSL], lastslot[NSL];
         float om0[NSL], aqm[NSL], omm[NSL];
 #pragma unroll
         for (int q = 0; q < NSL; q++) {
@@ -491,25 +479,28 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
             const int j = 1 + __clz(~((unsigned)p << (32 - LOGCH)));     // stage owning slot p
             mst[q] = j;
             mok[q] = (j < JR) && (j <= n_oct - 1);
-            gsz[q] = CH >> j;
-            firstslot[q] = (p == CH - 2 * (CH >> j));
             lastslot[q] = (p == CH - (CH >> j) - 1);
             om0[q] = P.om0[q][lane];
             aqm[q] = P.aqm[q][lane];
             omm[q] = P.omm[q][lane];
-#pragma unroll
+#pragma unroll 1
             for (int cc = 0; cc < NCH; cc++) {
                 const float *e0 = a.ema + (size_t)chan_first(cc) * nbands;
                 const float *e1 = a.ema + (size_t)chan_second(cc) * nbands;
+                T *ac = smem + cc * LY::STR + LY::ACC;
 #pragma unroll
                 for (int b = 0; b < BPO; b++) {
-                    v_set(acc0[cc][b][q], 0.f, 0.f);
-                    v_set(accm[cc][b][q], 0.f, 0.f);
-                    if (p == CH - 1) v_set(acc0[cc][b][q], e0[b], e1[b]);
-                    if (mok[q] && lastslot[q]) v_set(accm[cc][b][q], e0[j * BPO + b], e1[j * BPO + b]);
+                    T z0, zm;
+                    v_set(z0, 0.f, 0.f);
+                    v_set(zm, 0.f, 0.f);
+                    if (p == CH - 1) v_set(z0, e0[b], e1[b]);
+                    if (mok[q] && lastslot[q]) v_set(zm, e0[j * BPO + b], e1[j * BPO + b]);
+                    ac[b * CH + p] = z0;
+                    ac[(BPO + b) * CH + p] = zm;
                 }
             }
         }
+        __syncwarp();
         const int fdelta = P.fdelta;
         for (int k = 0; k < n_steps; k++) {
             const int kk = k - 1;              // the section warps' step whose band outputs are smoothed now
@@ -518,40 +509,49 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
 #pragma unroll
             for (int q = 0; q < NSL; q++) vm[q] = mok[q] && (unsigned)(kk - DEC_DEPTH * mst[q]) < (unsigned)n_chunks;
             const int buf = (kk & 1) * CH;
-#pragma unroll
+#pragma unroll 1
             for (int cc = 0; cc < NCH; cc++) {
                 const T *wb = smem + cc * LY::STR + LY::W + buf;
+                T *ac = smem + cc * LY::STR + LY::ACC;
 #pragma unroll
                 for (int b = 0; b < BPO; b++) {
 #pragma unroll
                     for (int q = 0; q < NSL; q++) {
-                        const T y0 = wb[b * LY::WSTR + lane + 32 * q];
-                        const T ym = wb[(NR + b) * LY::WSTR + lane + 32 * q];
-                        if (valid0) acc0[cc][b][q] = v_add(v_fma(-P.aq0, acc0[cc][b][q], acc0[cc][b][q]), v_sq(y0));
-                        if (vm[q]) accm[cc][b][q] = v_add(v_fma(-aqm[q], accm[cc][b][q], accm[cc][b][q]), v_sq(ym));
+                        const int p = lane + 32 * q;
+                        const T y0 = wb[b * LY::WSTR + p];
+                        const T ym = wb[(NR + b) * LY::WSTR + p];
+                        const T a0 = ac[b * CH + p];
+                        const T am = ac[(BPO + b) * CH + p];
+                        if (valid0) ac[b * CH + p] = v_add(v_fma(-P.aq0, a0, a0), v_sq(y0));
+                        if (vm[q]) ac[(BPO + b) * CH + p] = v_add(v_fma(-aqm[q], am, am), v_sq(ym));
                     }
                 }
             }
             // ---- block ends (warp-uniform conditions: they depend on the step only)
             if (valid0 && (((kk + 1) & nbmask) == 0)) {     // stage 0: weighted sum of its CH accumulators
                 const int blk = ((kk + 1) >> lognb) - 1;
-#pragma unroll
+#pragma unroll 1
                 for (int cc = 0; cc < NCH; cc++) {
+                    T *ac = smem + cc * LY::STR + LY::ACC;
+                    T *en = smem + cc * LY::STR + LY::EN + (blk & (EN_RING - 1)) * 32 + (n_oct - 1) * BPO;
 #pragma unroll
                     for (int b = 0; b < BPO; b++) {
-                        T val = v_fma(-om0[0], acc0[cc][b][0], acc0[cc][b][0]);
+                        T val;
+                        v_set(val, 0.f, 0.f);
 #pragma unroll
-                        for (int q = 1; q < NSL; q++) val = v_add(val, v_fma(-om0[q], acc0[cc][b][q], acc0[cc][b][q]));
+                        for (int q = 0; q < NSL; q++) {
+                            const T a0 = ac[b * CH + lane + 32 * q];
+                            val = v_add(val, v_fma(-om0[q], a0, a0));
+                        }
 #pragma unroll
                         for (int dlt = 16; dlt >= 1; dlt >>= 1) val = v_add(val, v_shfl_xor(val, dlt));
 #pragma unroll
                         for (int q = 0; q < NSL; q++) {
-                            v_set(acc0[cc][b][q], 0.f, 0.f);
-                            if (lane + 32 * q == CH - 1) acc0[cc][b][q] = val;
+                            T z;
+                            v_set(z, 0.f, 0.f);
+                            ac[b * CH + lane + 32 * q] = (lane + 32 * q == CH - 1) ? val : z;
                         }
-                        if (lane == 0)
-                            smem[cc * LY::STR + LY::EN + (blk & (EN_RING - 1)) * 32 + (n_oct - 1) * BPO + b] =
-                                v_mul(P.alpha[0] * P.gband[b] * P.gband[b], val);
+                        if (lane == 0) en[b] = v_mul(P.alpha[0] * P.gband[b] * P.gband[b], val);
                     }
                 }
             }
@@ -564,39 +564,30 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
                 const int len = CH >> j, lo = CH - 2 * len;          // slots [lo, lo + len)
                 const int kb0 = (n_oct - 1 - j) * BPO;
                 const float alj = sAl[j];
-#pragma unroll
+                const int ql = lo >> 5;                              // register (slot / 32) that holds the stage
+                const int l0 = lo & 31;
+                const bool mine = lane >= l0 && lane < l0 + len;
+#pragma unroll 1
                 for (int cc = 0; cc < NCH; cc++) {
+                    T *ac = smem + cc * LY::STR + LY::ACC + BPO * CH + 32 * ql + lane;
+                    T *en = smem + cc * LY::STR + LY::EN + (blk & (EN_RING - 1)) * 32 + kb0;
 #pragma unroll
                     for (int b = 0; b < BPO; b++) {
                         T val;
-                        if (len >= 32) {
-                            // CH = 64, stage 1: slots 0..31 = register 0 of every lane
-                            val = v_fma(-omm[0], accm[cc][b][0], accm[cc][b][0]);
+                        v_set(val, 0.f, 0.f);
+                        if (mine) {
+                            const T am = ac[b * CH];
+                            val = v_fma(-omm[ql], am, am);
+                        }
 #pragma unroll
-                            for (int dlt = 16; dlt >= 1; dlt >>= 1) val = v_add(val, v_shfl_xor(val, dlt));
-                            v_set(accm[cc][b][0], 0.f, 0.f);
-                            if (lane == 31) accm[cc][b][0] = val;
-                            if (lane == 0)
-                                smem[cc * LY::STR + LY::EN + (blk & (EN_RING - 1)) * 32 + kb0 + b] =
-                                    v_mul(alj * P.gband[b] * P.gband[b], val);
-                        } else {
-                            // the stage sits in lanes [lo & 31, (lo & 31) + len) of the last register
-                            constexpr int ql = NSL - 1;
-                            const int l0 = lo & 31;
-                            const bool mine = lane >= l0 && lane < l0 + len;
-                            v_set(val, 0.f, 0.f);
-                            if (mine) val = v_fma(-omm[ql], accm[cc][b][ql], accm[cc][b][ql]);
-#pragma unroll
-                            for (int dlt = 1; dlt < 16; dlt <<= 1) {
-                                if (dlt < len) val = v_add(val, v_shfl_xor(val, dlt));
-                            }
-                            if (mine) {
-                                v_set(accm[cc][b][ql], 0.f, 0.f);
-                                if (lane == l0 + len - 1) accm[cc][b][ql] = val;
-                                if (lane == l0)
-                                    smem[cc * LY::STR + LY::EN + (blk & (EN_RING - 1)) * 32 + kb0 + b] =
-                                        v_mul(alj * P.gband[b] * P.gband[b], val);
-                            }
+                        for (int dlt = 1; dlt < 32; dlt <<= 1) {
+                            if (dlt < len) val = v_add(val, v_shfl_xor(val, dlt));
+                        }
+                        if (mine) {
+                            T z;
+                            v_set(z, 0.f, 0.f);
+                            ac[b * CH] = (lane == l0 + len - 1) ? val : z;
+                            if (lane == l0) en[b] = v_mul(alj * P.gband[b] * P.gband[b], val);
                         }
                     }
                 }
@@ -606,14 +597,14 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
                 const int blk = ((k - fdelta) >> lognb) - 1;
                 __syncwarp();
                 if (lane < nbands) {
-#pragma unroll
+                    const float w = (a.db && a.weight) ? __ldg(a.weight + lane) : 0.f;
+#pragma unroll 1
                     for (int cc = 0; cc < NCH; cc++) {
                         if (chan_alive(cc)) {
                             const T v = smem[cc * LY::STR + LY::EN + (blk & (EN_RING - 1)) * 32 + lane];
                             float *o = a.energies + ((size_t)chan_first(cc) * a.n_blocks + blk) * nbands + lane;
                             float e0 = v_x(v), e1 = v_y(v);
                             if (a.db) {     // friture/octavespectrum.py:119-121: 10*log10(sp + 1e-30) + w
-                                const float w = a.weight ? __ldg(a.weight + lane) : 0.f;
                                 e0 = fmaf(3.01029995663981195f, lg2_fast(e0 + 1e-30f), w);
                                 e1 = fmaf(3.01029995663981195f, lg2_fast(e1 + 1e-30f), w);
                             }
@@ -627,30 +618,33 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
             cp_async_wait<PF - 1>();           // chunk k+1 has landed
             __syncthreads();
         }
-        // ---- epilogue: every chunked stage ended on a block boundary, its energy sits in one lane
+        // ---- epilogue: every chunked stage ended on a block boundary, its energy sits in one slot
+        __syncwarp();
 #pragma unroll
         for (int q = 0; q < NSL; q++) {
             const int p = lane + 32 * q;
-#pragma unroll
+#pragma unroll 1
             for (int cc = 0; cc < NCH; cc++) {
                 if (!chan_alive(cc)) continue;
                 float *e0 = a.ema + (size_t)chan_first(cc) * nbands;
                 float *e1 = a.ema + (size_t)chan_second(cc) * nbands;
                 const bool two = PACK == 2 && chan_second(cc) != chan_first(cc);
+                const T *ac = smem + cc * LY::STR + LY::ACC;
 #pragma unroll
                 for (int b = 0; b < BPO; b++) {
                     if (p == CH - 1) {
-                        e0[b] = v_x(acc0[cc][b][q]);
-                        if (two) e1[b] = v_y(acc0[cc][b][q]);
+                        const T v = ac[b * CH + p];
+                        e0[b] = v_x(v);
+                        if (two) e1[b] = v_y(v);
                     }
                     if (mok[q] && lastslot[q]) {
-                        e0[mst[q] * BPO + b] = v_x(accm[cc][b][q]);
-                        if (two) e1[mst[q] * BPO + b] = v_y(accm[cc][b][q]);
+                        const T v = ac[(BPO + b) * CH + p];
+                        e0[mst[q] * BPO + b] = v_x(v);
+                        if (two) e1[mst[q] * BPO + b] = v_y(v);
                     }
                 }
             }
         }
-        (void)gsz; (void)firstslot; (void)FULL;
     }
 }
 
