@@ -795,8 +795,12 @@ extern "C" int frt_bank_process(frt_handle h, const float *x_dev, int64_t x_stri
     bool use_pipe = pl->pipe_ok && !y_dev && pow2 && (block >> (P.n_oct - 1)) >= 1;
     if (force_k && force_k[0] == 's') use_pipe = false;
     if (use_pipe) {
-        int pack = pl->n_channels >= 2048 ? 2 : 1;
-        int logch = block >= 512 ? 6 : 5;   // must not depend on n_blocks: a stream gives the same bits however it is cut into launches
+        // measured on B200 (blocks/s of 512 samples, 27 bands): 1024 channels 5.2e7 / 6.8e7 with 32- /
+        // 64-sample steps, 8192 channels 1.31e8 / 1.10e8; packing two channels per lane (FFMA2) halves
+        // the warps and never paid.  The choice depends on the plan and the block length only, so a
+        // stream gives the same bits however it is cut into launches.
+        int pack = 1;
+        int logch = (block >= 512 && pl->n_channels <= 3072) ? 6 : 5;
         if (force_p) pack = force_p[0] == '2' ? 2 : 1;
         if (force_c) logch = force_c[0] == '6' ? 6 : 5;
         if (block < (1 << logch) * 4) logch = 5;

@@ -43,7 +43,6 @@ struct PipeParams {
     float aqm[2][32];           // multiplexed vector: 1 - q_j^len_j of the slot's stage j
     float omm[2][32];           // 1 - q_j^(len_j-1-pos)
     int T[BANK_MAX_OCT + 1];    // step at which stage j's chain heads start (pipe_schedule)
-    int fdelta;                 // steps after a block's last chunk until its band vector is flushed
     int n_oct, bpo;
 };
 
@@ -83,5 +82,4 @@ struct BankPlan {
 void frt_pipe_prepare(BankPlan *pl);
 void frt_pipe_schedule(int n_oct, int logch, long long t_total, int *T /*[BANK_MAX_OCT+1]*/,
                        int *n_steps);
-int frt_pipe_flush_delta(int n_oct, int logch, const int *T);
 cudaError_t frt_pipe_launch(const BankPlan *pl, BankArgs a, int logch, int pack, cudaStream_t st);

@@ -51,17 +51,7 @@ def n_steps_for(n_oct, logch, t_total, T):
         else:
             m_last = (t_total >> j) - 1
             last = max(last, T[j] + (m_last << (j - logch)) + dmax)
-    # the smoothing warp runs one step behind the section warps and flushes block b at step
-    # (b+1)*NB + delta (flush_delta below)
-    return max(last + 1, n_chunks + flush_delta(n_oct, logch, T)) + 1
-
-
-def flush_delta(n_oct, logch, T):
-    """Steps after a block's last stage-0 chunk until every stage has staged its band energies."""
-    delta = 0
-    for j in range(1, n_oct):
-        delta = max(delta, T[j] if j <= logch else T[j] - (1 << (j - logch)) + 1)
-    return delta
+    return last + 1
 
 
 def ctz(v):
