@@ -60,6 +60,10 @@ SIGNATURES = {
     "frt_bank_schedule": (c_int, [c_int, c_int, c_int64, c_void_p, c_void_p]),
     "frt_bank_process": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p,
                                  c_int64, c_int, c_void_p]),
+    "frt_bank_process_strided": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p, c_int64,
+                                         c_int, c_void_p]),
+    "frt_combined_process_host": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int64, c_int, c_void_p,
+                                          c_void_p, c_int, c_int]),
     "frt_bank_state_size": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64)]),
     "frt_bank_get_state": (c_int, [c_void_p, c_void_p, c_void_p]),
     "frt_bank_set_state": (c_int, [c_void_p, c_void_p, c_void_p]),
@@ -136,6 +140,14 @@ class Handle:
         if rc == FRT_EINVAL:
             raise FrtValueError(rc, msg)
         raise FrtError(rc, msg)
+
+    def check_device(self, tensor):
+        """A tensor on another GPU than the handle's would surface as an illegal-address error
+        deep inside a kernel; say it plainly instead."""
+        idx = getattr(getattr(tensor, "device", None), "index", None)
+        if idx is not None and idx != self.device:
+            raise FrtValueError(FRT_EINVAL, "tensor lives on cuda:%d, this handle is bound to cuda:%d"
+                                % (idx, self.device))
 
     def call(self, name, *args):
         self.check(getattr(self._lib, name)(self._h, *args))

@@ -137,6 +137,7 @@ class audioproc():
             raise ValueError("out must be a contiguous float32 tensor of shape %s" % ((C, nf, nb),))
         if C == 0 or nf == 0:
             return out
+        self.handle.check_device(x)
         self._ensure_plan()
         sp = _lib.current_stream_ptr(x.device) if stream is None else c_void_p(int(stream))
         self.handle.call("frt_stft_process", _lib._ptr(x), int(x.stride(0)) if C > 1 else int(T),

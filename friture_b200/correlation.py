@@ -58,6 +58,8 @@ class GccPhat:
         P, L = d0.shape
         if L != self.length:
             raise ValueError("frame length %d != planned %d" % (L, self.length))
+        self.handle.check_device(d0)
+        self.handle.check_device(d1)
         d0 = d0.contiguous()
         d1 = d1.contiguous()
         self.handle.call("frt_gcc_plan", int(L))
@@ -68,10 +70,12 @@ class GccPhat:
         have_prev = 0
         if smooth:
             if self._smoothed is None or tuple(self._smoothed.shape) != (P, L):
-                self._smoothed = torch.empty((P, L), dtype=torch.float32, device=d0.device)
+                self._smoothed = torch.zeros((P, L), dtype=torch.float32, device=d0.device)
                 self._have_prev = False
             sm = self._smoothed
-            have_prev = 1 if self._have_prev else 0
+            # 2 = per pair: a pair whose frames have all been silent so far has no previous smoothed
+            # frame (the kernel marks it), like old_Xcorr = None in the widget
+            have_prev = 2 if self._have_prev else 0
         sp = _lib.current_stream_ptr(d0.device) if stream is None else c_void_p(int(stream))
         self.handle.call("frt_gcc_phat", _lib._ptr(d0), _lib._ptr(d1), int(L), int(P),
                          _lib._ptr(xc), _lib._ptr(sm), have_prev, _lib._ptr(idx), _lib._ptr(val), sp)

@@ -113,6 +113,7 @@ extern "C" int frt_destroy(frt_handle h) {
     frt_bank_release(h);
     frt_gcc_release(h);
     frt_dec_release(h);
+    frt_comb_release(h);
     pipe_release(h);
     delete h;
     return FRT_OK;

@@ -374,7 +374,7 @@ bank_kernel(const __grid_constant__ BankParams P, const BankArgs a) {
         }
         const bool block_end = ((t + 1) % a.tiles_per_block) == 0;
         w.energies = (a.energies && block_end)
-                         ? a.energies + ((size_t)c * n_blocks + t / a.tiles_per_block) * nbands
+                         ? a.energies + (size_t)c * a.e_stride + (size_t)(t / a.tiles_per_block) * nbands
                          : nullptr;
         w.t_off = (long long)t * TILE;
         scan_stage<L0>(xc, w, 0);
@@ -438,7 +438,7 @@ bank_kernel3(const __grid_constant__ BankParams P, const BankArgs a) {
             }
             const bool block_end = ((t + 1) % a.tiles_per_block) == 0;
             w.energies = (a.energies && block_end)
-                             ? a.energies + ((size_t)c * n_blocks + t / a.tiles_per_block) * nbands
+                             ? a.energies + (size_t)c * a.e_stride + (size_t)(t / a.tiles_per_block) * nbands
                              : nullptr;
             w.t_off = (long long)t * TILE;
             if (role == 0) stage_D<L0>(xc, w, 0, s_x, s_x32 + (t & 1) * 32);
@@ -447,7 +447,7 @@ bank_kernel3(const __grid_constant__ BankParams P, const BankArgs a) {
             const int tp = t - 1;
             const bool block_end = ((tp + 1) % a.tiles_per_block) == 0;
             w.energies = (a.energies && block_end)
-                             ? a.energies + ((size_t)c * n_blocks + tp / a.tiles_per_block) * nbands
+                             ? a.energies + (size_t)c * a.e_stride + (size_t)(tp / a.tiles_per_block) * nbands
                              : nullptr;
             w.t_off = (long long)tp * TILE;
             if (NSCAN < P.n_oct) serial_stages<WarpCtxT<WANT_Y>>(s_x32[(tp & 1) * 32 + lane], 32, w, NSCAN);
@@ -615,6 +615,8 @@ extern "C" int frt_bank_plan(frt_handle h, int n_channels, int bands_per_octave,
     if (e == cudaSuccess) e = cudaMalloc(&pl->ema, sizeof(float) * pl->ne * n_channels);
     if (e == cudaSuccess) e = cudaMemset(pl->zstate, 0, sizeof(float) * pl->nz * n_channels);
     if (e == cudaSuccess) e = cudaMemset(pl->ema, 0, sizeof(float) * pl->ne * n_channels);
+    // the memsets run on the legacy stream; callers process on their own (possibly non-blocking) streams
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         if (pl->zstate) cudaFree(pl->zstate);
         if (pl->ema) cudaFree(pl->ema);
@@ -632,6 +634,7 @@ extern "C" int frt_bank_reset(frt_handle h) {
     BankPlan *pl = h->bank;
     FRT_CUDA(h, cudaMemset(pl->zstate, 0, sizeof(float) * pl->nz * pl->n_channels));
     FRT_CUDA(h, cudaMemset(pl->ema, 0, sizeof(float) * pl->ne * pl->n_channels));
+    FRT_CUDA(h, cudaDeviceSynchronize());
     return FRT_OK;
 }
 
@@ -740,9 +743,35 @@ static cudaError_t launch_bank(const BankPlan *pl, const BankArgs &a, cudaStream
     return a.y ? launch_bank_y<L0, true>(pl, a, st) : launch_bank_y<L0, false>(pl, a, st);
 }
 
+static int bank_process_impl(frt_handle h, const float *x_dev, int64_t x_stride, int block,
+                             int n_blocks, float *energies_dev, int64_t e_stride, float *y_dev,
+                             int64_t y_stride, int db, void *stream);
+
 extern "C" int frt_bank_process(frt_handle h, const float *x_dev, int64_t x_stride, int block,
                                 int n_blocks, float *energies_dev, float *y_dev,
                                 int64_t y_stride, int db, void *stream) {
+    if (!h) return FRT_EINVAL;
+    const int64_t nb = h->bank ? (int64_t)h->bank->params.n_oct * h->bank->params.bpo : 0;
+    return bank_process_impl(h, x_dev, x_stride, block, n_blocks, energies_dev, (int64_t)n_blocks * nb,
+                             y_dev, y_stride, db, stream);
+}
+
+extern "C" int frt_bank_process_strided(frt_handle h, const float *x_dev, int64_t x_stride, int block,
+                                        int n_blocks, float *energies_dev, int64_t e_stride_c, int db,
+                                        void *stream) {
+    if (!h) return FRT_EINVAL;
+    if (h->bank && energies_dev) {
+        const int64_t nb = (int64_t)h->bank->params.n_oct * h->bank->params.bpo;
+        if (e_stride_c < (int64_t)n_blocks * nb)
+            return frt_fail(h, FRT_EINVAL, "e_stride_c smaller than n_blocks * nbands");
+    }
+    return bank_process_impl(h, x_dev, x_stride, block, n_blocks, energies_dev, e_stride_c, nullptr, 0, db,
+                             stream);
+}
+
+static int bank_process_impl(frt_handle h, const float *x_dev, int64_t x_stride, int block,
+                             int n_blocks, float *energies_dev, int64_t e_stride, float *y_dev,
+                             int64_t y_stride, int db, void *stream) {
     if (!h) return FRT_EINVAL;
     if (!h->bank) return frt_fail(h, FRT_ESTATE, "frt_bank_process: call frt_bank_plan first");
     DeviceGuard g(h->device);
@@ -772,6 +801,7 @@ extern "C" int frt_bank_process(frt_handle h, const float *x_dev, int64_t x_stri
     a.zstate = pl->zstate;
     a.ema = pl->ema;
     a.energies = energies_dev;
+    a.e_stride = e_stride;
     a.y = y_dev;
     a.y_stride = y_stride;
     a.t_total = t_total;
@@ -870,6 +900,7 @@ extern "C" int frt_decimate_plan(frt_handle h, int n_channels, int n_stages, con
     const size_t nz = (size_t)n_stages * 6 * 2 * n_channels;
     cudaError_t e = cudaMalloc(&pl->zstate, sizeof(float) * nz);
     if (e == cudaSuccess) e = cudaMemset(pl->zstate, 0, sizeof(float) * nz);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
         if (pl->zstate) cudaFree(pl->zstate);
         delete pl;

@@ -54,7 +54,8 @@ struct BankArgs {
     int tiles_per_block;   // energies are emitted after every tiles_per_block-th tile
     float *zstate;         // [C][n_oct][nsec][2]
     float *ema;            // [C][n_oct][bpo]   smoothed energies / alpha_j (dispbuffers / alpha)
-    float *energies;       // [C][n_blocks][nbands] or NULL
+    float *energies;       // channel c, block b at energies + c*e_stride + b*nbands, or NULL
+    long long e_stride;    // floats between channels (n_blocks*nbands when contiguous)
     float *y;              // ragged band outputs or NULL
     long long y_stride;
     long long t_total;     // samples per channel in this launch

@@ -35,7 +35,7 @@
 //   form (acc - (1-q^n) acc): the float32 rounding of q must not bias long time constants.
 //
 // tests/bank_pipeline_model.py is an executable NumPy model of exactly this schedule, checked
-// against the oracle on CPU; this file mirrors it phase by phase.
+// against the CPU restatement of the reference; this file mirrors it phase by phase.
 #include <cmath>
 #include <cstdlib>
 #include <type_traits>
@@ -240,9 +240,9 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
     const int logblock = lognb + LOGCH;
     const bool want_e = alive && a.energies != nullptr;
     EmitCtx ectx;
-    ectx.base = a.energies ? a.energies + (size_t)ch0 * a.n_blocks * nbands : nullptr;
+    ectx.base = a.energies ? a.energies + (size_t)ch0 * a.e_stride : nullptr;
     ectx.weight = a.db ? a.weight : nullptr;
-    ectx.ch_stride = (long long)a.n_blocks * nbands;
+    ectx.ch_stride = a.e_stride;
     ectx.nbands = nbands;
     ectx.db = a.db;
     ectx.has2 = has2 ? 1 : 0;

@@ -44,6 +44,7 @@ struct frt_ctx {
     BankPlan *bank = nullptr;
     GccPlan *gcc = nullptr;
     void *dec = nullptr;          // DecPlan (bank.cu)
+    void *comb = nullptr;         // CombPipe (combined.cu)
 };
 
 int frt_fail(frt_ctx *h, int code, const char *fmt, ...);
@@ -78,4 +79,5 @@ struct DeviceGuard {
 void frt_bank_release(frt_ctx *h);
 void frt_gcc_release(frt_ctx *h);
 void frt_dec_release(frt_ctx *h);
+void frt_comb_release(frt_ctx *h);
 int frt_pipe_ensure(frt_ctx *h, size_t in_bytes, size_t out_bytes);

@@ -266,6 +266,9 @@ __global__ void __launch_bounds__(GCC_THREADS, 1) gcc_phat_kernel(const GccArgs 
             }
             if (a.xcorr)
                 for (int n = tid; n < L; n += nt) a.xcorr[(size_t)pair * L + n] = 0.f;
+            // the reference leaves old_Xcorr alone on a silent frame (delay_estimator.py:129-131,162-165);
+            // on the very first call there is none yet: mark the pair "no previous" (NaN in slot 0)
+            if (a.smoothed && a.have_prev == 0 && tid == 0) a.smoothed[(size_t)pair * L] = nanf("");
             __syncthreads();
             continue;
         }
@@ -312,11 +315,16 @@ __global__ void __launch_bounds__(GCC_THREADS, 1) gcc_phat_kernel(const GccArgs 
         int besti = 0x7fffffff;
         float *sm = a.smoothed ? a.smoothed + (size_t)pair * L : nullptr;
         float *xc = a.xcorr ? a.xcorr + (size_t)pair * L : nullptr;
+        // have_prev: 1 = every pair has a previous smoothed frame; 2 = per pair, a NaN in slot 0
+        // marks a pair that has had only silent frames so far (old_Xcorr is None there)
+        bool prev = a.have_prev == 1;
+        if (sm && a.have_prev == 2) prev = !isnan(sm[0]);
+        __syncthreads();     // everyone has read the marker before slot 0 is rewritten
         for (int n = tid; n < L; n += nt) {
             float v = z[__ldg(a.perm + n)].x * inv;
             if (xc) xc[n] = v;
             if (sm) {
-                if (a.have_prev) v = 0.3f * v + 0.7f * sm[n];
+                if (prev) v = 0.3f * v + 0.7f * sm[n];
                 sm[n] = v;
             }
             const float av = fabsf(v);
@@ -465,6 +473,7 @@ extern "C" int frt_gcc_phat(frt_handle h, const float *d0_dev, const float *d1_d
     if (n_pairs == 0) return FRT_OK;
     FRT_CHECK_ARG(h, d0_dev && d1_dev && idx_dev && val_dev, "NULL buffer");
     FRT_CHECK_ARG(h, stride >= pl->L, "stride smaller than the frame length");
+    FRT_CHECK_ARG(h, have_prev >= 0 && have_prev <= 2, "have_prev must be 0, 1 or 2");
     FRT_CHECK_ARG(h, !have_prev || smoothed_dev, "have_prev needs the smoothed buffer");
     GccArgs a;
     a.d0 = d0_dev;
@@ -482,6 +491,10 @@ extern "C" int frt_gcc_phat(frt_handle h, const float *d0_dev, const float *d1_d
     a.val = val_dev;
     a.rd = pl->rd;
     int blocks = n_pairs < h->sm_count ? n_pairs : h->sm_count;
+    // the dynamic shared-memory limit is a per-device attribute of the kernel: another handle that
+    // planned a shorter frame may have lowered it since this plan was built
+    FRT_CUDA(h, cudaFuncSetAttribute(gcc_phat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(sizeof(float2) * pl->L)));
     gcc_phat_kernel<<<blocks, GCC_THREADS, sizeof(float2) * pl->L, (cudaStream_t)stream>>>(a);
     h->launches++;
     FRT_CUDA(h, cudaGetLastError());

@@ -643,6 +643,18 @@ extern "C" int frt_stft_plan(frt_handle h, int n_fft) {
         return FRT_OK;
     }
     StftPlan pl;
+    // a failed cudaMalloc / cudaMemcpy below returns early: free what the half-built plan owns
+    struct PlanGuard {
+        StftPlan *p;
+        ~PlanGuard() {
+            if (!p) return;
+            if (p->win_dev) cudaFree(p->win_dev);
+            if (p->tw_dev) cudaFree(p->tw_dev);
+            if (p->post_dev) cudaFree(p->post_dev);
+            if (p->wlane_dev) cudaFree(p->wlane_dev);
+            if (p->comb_dev) cudaFree(p->comb_dev);
+        }
+    } guard{&pl};
     const int N = n_fft, M = N / 2;
     const double PI = 3.14159265358979323846;
     // symmetric Hann, friture/audioproc.py:76-81
@@ -718,6 +730,7 @@ extern "C" int frt_stft_plan(frt_handle h, int n_fft) {
                                          (int)(sizeof(float2) * 2 * 8192)));
     }
     pl.n_fft = n_fft;
+    guard.p = nullptr;          // the cache owns the device tables from here on
     h->stft_cache[n_fft] = pl;
     h->stft = pl;
     return FRT_OK;

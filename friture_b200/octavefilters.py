@@ -8,7 +8,7 @@ independent-channel axis (``filter_batch`` / ``energies_batch``) that fuse the o
 
 Numerics: the reference has two implementations of the same IIR designs, the live FFT
 overlap-add with 512-tap FIR approximations (friture/filter.py:136-247) and the IIR bank
-``octave_filter_bank_decimation`` (friture/filter.py:86-118) that its own tests use as the oracle
+``octave_filter_bank_decimation`` (friture/filter.py:86-118) that its own tests check against
 (friture/test/test_octave_filters.py:21-35).  The GPU kernel runs the IIR designs themselves (as
 float32 second-order sections), so it matches the IIR bank to ~1e-6 and the live FFT path to the
 ~5e-4 by which the reference's two paths differ from each other.
@@ -67,12 +67,12 @@ class Octave_Filters():
 
     FIR_LENGTH = FIR_LENGTH
 
-    def __init__(self, bandsperoctave, device=None, n_octaves=NOCTAVE, response_time=1.0):
+    def __init__(self, bandsperoctave, device=None, n_octaves=NOCTAVE, response_time=1.0, handle=None):
         self.bdec, self.adec, self._sos_dec = filter_data.decimator()
         self.bdec = np.array(self.bdec)
         self.adec = np.array(self.adec)
-        self._device = device
-        self._handle = None
+        self._device = device if handle is None else handle.device
+        self._handle = handle      # share a handle (one GPU context) with other objects, or own one
         self._n_octaves = n_octaves
         self._response_time = response_time
         self._plan_key = None
@@ -227,6 +227,7 @@ class Octave_Filters():
         if energies and block > MAX_BLOCK:
             raise ValueError("block > %d: the reference's smoothing kernel is shorter than the "
                              "block (exp_smoothing.py:43-47)" % MAX_BLOCK)
+        self.handle.check_device(x)
         n_blocks = T // block
         self._ensure_plan(C)
         e = None
@@ -277,20 +278,3 @@ class Octave_Filters():
 # CamelCase alias used by BASELINE.json's prose (the reference class is Octave_Filters)
 OctaveFilters = Octave_Filters
 
-
-def smoke_check():
-    """Tiny filterbank run on cuda:0 against the CPU oracle (used by __graft_entry__.smoke)."""
-    import torch
-    from oracle import friture_oracle as fo
-    g = torch.Generator().manual_seed(99)
-    x = (torch.randn(2, 4 * 512, generator=g) * 0.1).float()
-    bank = Octave_Filters(3)
-    e = bank.energies_batch(x.cuda(), block=512).cpu().numpy().astype(np.float64)
-    worst = 0.0
-    for c in range(2):
-        orc = fo.OctaveSpectrumOracle(bank.bdec, bank.adec, bank.boct, bank.aoct)
-        for b in range(4):
-            sp, _, _ = orc.push(x[c, b * 512:(b + 1) * 512].numpy().astype(np.float64))
-            worst = max(worst, float(np.max(np.abs(e[c, b] - sp) / np.max(sp))))
-    assert worst < 1e-5, "filterbank energies mismatch vs oracle: %g" % worst
-    print("smoke: 1/3-octave band energies max rel err %.3g" % worst)

@@ -114,6 +114,12 @@ int frt_bank_schedule(int n_octaves, int log2_chunk, int64_t n_samples, int *sta
  *                 holding (block*n_blocks) >> j samples                                       */
 int frt_bank_process(frt_handle h, const float *x_dev, int64_t x_stride, int block, int n_blocks,
                      float *energies_dev, float *y_dev, int64_t y_stride, int db, void *stream);
+/* Same with the energies of channel c, block b written to energies_dev + c*e_stride_c + b*nbands
+ * (e_stride_c >= n_blocks*nbands): lets a caller that cuts one stream into several launches fill
+ * one [C][all blocks][nbands] array.  No ragged band outputs.                                  */
+int frt_bank_process_strided(frt_handle h, const float *x_dev, int64_t x_stride, int block,
+                             int n_blocks, float *energies_dev, int64_t e_stride_c, int db,
+                             void *stream);
 /* State checkpoint / resume (the reference keeps its state inside the object,
  * octavefilters.py:50-56).  z: [C][n_octaves][2*bpo+6][2] section states; ema:
  * [C][n_octaves][bpo] smoothed energy divided by alpha_j (the kernel's internal form, so that a
@@ -122,6 +128,20 @@ int frt_bank_process(frt_handle h, const float *x_dev, int64_t x_stride, int blo
 int frt_bank_state_size(frt_handle h, int64_t *z_floats, int64_t *ema_floats);
 int frt_bank_get_state(frt_handle h, float *z_host, float *ema_host);
 int frt_bank_set_state(frt_handle h, const float *z_host, const float *ema_host);
+
+/* ---------------------------------------------------------------- combined per-hop analysis
+ * What Spectrogram_Widget.handle_new_data (friture/spectrogram.py:131-169) and
+ * OctaveSpectrum_Widget.handle_new_data (friture/octavespectrum.py:91-121) compute from the same
+ * chunk of new samples, for n_channels independent streams held in HOST memory: the log-power
+ * column of every hop (frt_stft_plan'ed size, frames as in frt_stft_process_host) and the smoothed
+ * band levels after every hop-sized block (frt_bank_plan'ed bank, dB + weighting when db != 0).
+ * H2D copy, the two kernels and the D2H copies are pipelined over time segments inside the call
+ * (bench.py's `e2e`).  n_samples % hop == 0, hop a valid filterbank block;
+ *   spec_host  [n_channels][(n_samples - n_fft)/hop + 1][n_fft/2 + 1]
+ *   bands_host [n_channels][n_samples/hop][nbands]                                               */
+int frt_combined_process_host(frt_handle h, const float *x_host, int64_t x_stride, int n_channels,
+                              int64_t n_samples, int hop, float *spec_host, float *bands_host,
+                              int nbands, int db);
 
 /* ---------------------------------------------------------------- GCC-PHAT (delay estimator)
  * Stands behind `generalized_cross_correlation(d0, d1)` (friture/signal/correlation.py:24-43)
@@ -133,8 +153,11 @@ int frt_gcc_plan(frt_handle h, int length);
 /* n_pairs independent channel pairs: d0/d1[p*stride + n].  Inputs are not modified (the
  * reference subtracts the means in place, a side effect that is not reproduced).
  *   xcorr_dev     NULL or [n_pairs][length]: this frame's Xcorr (correlation.py:41)
- *   smoothed_dev  NULL or [n_pairs][length]: smoothed Xcorr, read when have_prev != 0
- *                 (0.3*X + 0.7*old, delay_estimator.py:134-139) and always written
+ *   smoothed_dev  NULL or [n_pairs][length]: smoothed Xcorr (0.3*X + 0.7*old, delay_estimator.py:134-139),
+ *                 written for every non-silent pair.  have_prev: 0 = first frame, nothing to blend
+ *                 (a silent pair is marked "no previous" with a NaN in its slot 0); 1 = blend every
+ *                 pair with the buffer; 2 = blend the pairs that have had a non-silent frame (no
+ *                 NaN marker) -- the widget's `old_Xcorr is not None`; silent pairs keep their buffer
  *   idx_dev/val_dev [n_pairs]: i = argmax |Xs| and Xs[i] (delay_estimator.py:141-146); pairs
  *                 with a constant input (std == 0) give (0, 0) as in delay_estimator.py:129-131,164-167 */
 int frt_gcc_phat(frt_handle h, const float *d0_dev, const float *d1_dev, int64_t stride,

@@ -4,21 +4,26 @@ north_star: outputs match the reference "within 1e-5 relative float32 on the log
 band-energy vectors".  The relative error of a vector is max|got-ref| / max(max|ref|, 1)
 (SURVEY.md 8d).
 
-float32 arithmetic has an amplitude noise floor: a 2048-point float32 FFT carries an absolute
-error of about 2e-7 x (rms spectral amplitude of the frame) in every bin, whatever the bin's
-own level.  On the dB scale this is invisible for ordinary bins and unbounded for deep nulls
-(|X| -> 0), which occur with probability ~1e-4 per bin at -40 dB below the frame's mean power
-for broadband input.  The log-power criterion is therefore applied as is to bins no more than
-FLOOR_DB below the frame's mean power; every bin, nulls included, must stay within
-TOL*max|ref| + 20*log10(1 + AMP_TOL*rms/|X_ref|), i.e. the same tolerance widened by the dB
-image of an amplitude error of AMP_TOL x (frame rms) -- ~80 float32 epsilons, about 20x the rms
-rounding noise of an 11-stage float32 FFT.
+The criterion is asserted STRICTLY (`rel_all`, every bin) on broadband inputs of up to
+STRICT_MAX_BINS bins -- the sizes at which north_star's number is defined and measured (bench.py's
+parity gate, smoke()).  float32 arithmetic has an amplitude noise floor: a 2048-point float32 FFT
+carries an absolute error of about 2e-7 x (rms spectral amplitude of the frame) in every bin,
+whatever the bin's own level.  On the dB scale that stays below 1e-5 x max|ref| (about 1e-3 dB)
+only for bins above ~ -55 dB of the frame's mean power; for broadband input a bin falls below -50 dB
+with probability ~1e-5, so a sample of 1e7 bins is certain to contain dozens of such deep nulls
+where NO float32 transform can meet the dB criterion.  Large samples and tonal inputs are therefore
+judged bin by bin: the criterion as is for bins no more than FLOOR_DB below the frame's mean power
+(>= 99.99 % of the bins of a broadband input, reported), and for every bin, nulls included,
+TOL*max|ref| + 20*log10(1 + AMP_TOL*rms/|X_ref|), i.e. the same tolerance widened by the dB image
+of an amplitude error of AMP_TOL x (frame rms) -- ~80 float32 epsilons, about 20x the rms rounding
+noise of an 11-stage float32 FFT.
 """
 import numpy as np
 
 TOL = 1e-5        # relative error of the log-power / band-energy vector
-FLOOR_DB = 40.0   # log-power criterion applies down to this far below the frame's mean power
+FLOOR_DB = 50.0   # below ~this far under the frame mean power float32 cannot resolve 1e-3 dB
 AMP_TOL = 5e-6    # amplitude noise allowance for deep nulls, relative to the frame rms
+STRICT_MAX_BINS = 200000   # strict every-bin criterion up to this sample size
 
 
 def rel_err(got, ref):
@@ -54,14 +59,20 @@ def logpower_errors(got_db, ref_db, eps=1e-30):
     }
 
 
-def logpower_ok(e, min_frac=0.999):
-    return (e["rel_above_floor"] < TOL and e["worst_ratio_all"] < 1.0
-            and e["frac_above_floor"] >= min_frac)
+def logpower_ok(e, min_frac=0.9999, strict=False):
+    ok = (e["rel_above_floor"] < TOL and e["worst_ratio_all"] < 1.0
+          and e["frac_above_floor"] >= min_frac)
+    if strict:
+        ok = ok and e["rel_all"] < TOL
+    return ok
 
 
-def assert_logpower_parity(got_db, ref_db, min_frac=0.999):
-    """min_frac: broadband inputs must have (almost) every bin above the floor; tonal inputs,
-    whose mean power is dominated by a few bins, pass min_frac=0."""
+def assert_logpower_parity(got_db, ref_db, min_frac=0.9999, strict=None):
+    """Broadband inputs: strict every-bin criterion up to STRICT_MAX_BINS bins (strict=None picks
+    that), and (almost) every bin above the floor.  Tonal inputs, whose mean power is dominated by
+    a few bins, pass min_frac=0 and strict=False."""
     e = logpower_errors(got_db, ref_db)
-    assert logpower_ok(e, min_frac), e
+    if strict is None:
+        strict = np.asarray(ref_db).size <= STRICT_MAX_BINS and min_frac > 0
+    assert logpower_ok(e, min_frac, strict), e
     return e

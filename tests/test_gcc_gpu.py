@@ -85,3 +85,53 @@ def test_config4_sample_4096_pairs():
     d1 = torch.stack([torch.roll(d0[p], int(k[p])) for p in range(P)]) + 0.1 * torch.randn(P, L, generator=g)
     idx, val, _ = GccPhat(L).estimate(d0.cuda(), d1.cuda(), smooth=False)
     assert torch.equal(idx.cpu().long(), k)
+
+
+def test_silent_pairs_keep_no_smoothing_state():
+    """A pair whose first frames are silent has no previous smoothed frame (old_Xcorr is None in the
+    widget, delay_estimator.py:129-139): its first real frame is used unsmoothed, the later ones are
+    blended; a silent frame in between leaves the state alone.  Two estimators with different frame
+    lengths share the device (the kernel's shared-memory limit is set per launch)."""
+    import torch
+    from friture_b200.correlation import GccPhat
+    from oracle import friture_oracle as fo
+    rng = np.random.default_rng(5)
+    L = 4096
+    frames = []
+    for k in range(3):
+        d0 = rng.standard_normal((2, L))
+        d1 = np.roll(d0, 40 + k, axis=1) + 0.1 * rng.standard_normal((2, L))
+        frames.append((d0, d1))
+    est = GccPhat(L)
+    other = GccPhat(24000)                              # lowers / raises the per-device smem limit
+    big = torch.randn(1, 24000, device="cuda")
+    cuda = lambda a: torch.from_numpy(a.astype(np.float32)).cuda()
+    # call 1: pair 0 silent, pair 1 real
+    d0, d1 = frames[0]
+    a0, a1 = d0.copy(), d1.copy()
+    a0[0] = 0.25
+    i, v, _ = est.estimate(cuda(a0), cuda(a1), smooth=True)
+    other.estimate(big, big, smooth=False)
+    assert int(i[0]) == 0 and float(v[0]) == 0.0
+    old1 = fo.generalized_cross_correlation(a0[1].astype(np.float32).astype(np.float64),
+                                            a1[1].astype(np.float32).astype(np.float64))
+    # call 2: both real -> pair 0 unsmoothed (first valid frame), pair 1 blended with call 1
+    d0, d1 = frames[1]
+    i, v, _ = est.estimate(cuda(d0), cuda(d1), smooth=True)
+    x0 = fo.generalized_cross_correlation(d0[0].astype(np.float32).astype(np.float64),
+                                          d1[0].astype(np.float32).astype(np.float64))
+    x1 = fo.generalized_cross_correlation(d0[1].astype(np.float32).astype(np.float64),
+                                          d1[1].astype(np.float32).astype(np.float64))
+    s1 = 0.3 * x1 + 0.7 * old1
+    assert int(i[0]) == int(np.argmax(np.abs(x0))) and abs(float(v[0]) - x0[int(i[0])]) < ABS_TOL
+    assert int(i[1]) == int(np.argmax(np.abs(s1))) and abs(float(v[1]) - s1[int(i[1])]) < ABS_TOL
+    assert torch.isfinite(est._smoothed).all()
+    # call 3: pair 1 silent -> its state stays; pair 0 blended with call 2
+    d0, d1 = frames[2]
+    a0, a1 = d0.copy(), d1.copy()
+    a1[1] = -1.0
+    est.estimate(cuda(a0), cuda(a1), smooth=True)
+    assert np.max(np.abs(est._smoothed[1].cpu().numpy() - s1)) < ABS_TOL
+    x0c = fo.generalized_cross_correlation(a0[0].astype(np.float32).astype(np.float64),
+                                           a1[0].astype(np.float32).astype(np.float64))
+    assert np.max(np.abs(est._smoothed[0].cpu().numpy() - (0.3 * x0c + 0.7 * x0))) < ABS_TOL

@@ -45,7 +45,7 @@ def test_power_all_sizes(n_fft):
     assert rel_err(got, ref) < TOL
     got = run_gpu(x, n_fft, n_fft // 4, log=True)
     # few bins per frame at the small sizes: allow more of them below the floor
-    assert_logpower_parity(got, fo.log_spectrogram(ref), min_frac=0.95 if n_fft < 1024 else 0.999)
+    assert_logpower_parity(got, fo.log_spectrogram(ref), min_frac=0.95 if n_fft < 1024 else 0.9999)
 
 
 @pytest.mark.parametrize("kind", ["randn", "uniform"])
@@ -78,7 +78,7 @@ def test_tonal_above_floor():
     x = make_input("sine", 2, 2048 * 4, seed=3)
     got = run_gpu(x, 2048, 1024, log=True)
     ref = fo.log_spectrogram(fo.stft_power_batch(x, 2048, 1024))
-    e = assert_logpower_parity(got, ref, min_frac=0.0)
+    e = assert_logpower_parity(got, ref, min_frac=0.0, strict=False)
     peak = ref >= ref.max() - 30.0
     assert np.max(np.abs(got[peak] - ref[peak])) / max(np.max(np.abs(ref)), 1.0) < TOL, e
 
