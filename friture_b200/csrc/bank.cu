@@ -657,7 +657,7 @@ extern "C" int frt_bank_set_weighting(frt_handle h, const float *weight_db_host)
 
 extern "C" int frt_bank_schedule(int n_octaves, int log2_chunk, int64_t n_samples, int *stage_start,
                                  int *n_steps) {
-    if (n_octaves < 1 || n_octaves > MAX_OCT || (log2_chunk != 5 && log2_chunk != 6) || !stage_start ||
+    if (n_octaves < 1 || n_octaves > MAX_OCT || (log2_chunk < 5 || log2_chunk > 7) || !stage_start ||
         n_samples < 0)
         return FRT_EINVAL;
     int T[BANK_MAX_OCT + 1];
@@ -832,8 +832,9 @@ static int bank_process_impl(frt_handle h, const float *x_dev, int64_t x_stride,
         int pack = 1;
         int logch = (block >= 512 && pl->n_channels <= 3072) ? 6 : 5;
         if (force_p) pack = force_p[0] == '2' ? 2 : 1;
-        if (force_c) logch = force_c[0] == '6' ? 6 : 5;
-        if (block < (1 << logch) * 4) logch = 5;
+        if (force_c) logch = force_c[0] == '7' ? 7 : (force_c[0] == '6' ? 6 : 5);
+        while (logch > 5 && block < (4 << logch)) logch--;
+        if (logch == 7) pack = 1;
         e = frt_pipe_launch(pl, a, logch, pack, st);
     } else if (tile == 1024) e = launch_bank<32>(pl, a, st);
     else if (tile == 512) e = launch_bank<16>(pl, a, st);

@@ -39,10 +39,11 @@ struct PipeParams {
     float alpha[BANK_MAX_OCT + 1];
     // smoothing accumulators, one per sample slot of a step (slot = lane + 32*s):
     float aq0;                  // 1 - q_0^CH
-    float om0[2][32];           // 1 - q_0^(CH-1-slot)
-    float aqm[2][32];           // multiplexed vector: 1 - q_j^len_j of the slot's stage j
-    float omm[2][32];           // 1 - q_j^(len_j-1-pos)
+    float om0[4][32];           // 1 - q_0^(CH-1-slot)
+    float aqm[4][32];           // multiplexed vector: 1 - q_j^len_j of the slot's stage j
+    float omm[4][32];           // 1 - q_j^(len_j-1-pos)
     int T[BANK_MAX_OCT + 1];    // step at which stage j's chain heads start (pipe_schedule)
+    int fdelta;                 // steps after a block's last chunk until every stage has staged its energies
     int n_oct, bpo;
 };
 
@@ -69,7 +70,7 @@ struct BankArgs {
 
 struct BankPlan {
     BankParams params;
-    PipeParams pipe[2];    // [0]: 32-sample steps, [1]: 64-sample steps
+    PipeParams pipe[3];    // steps of 32, 64, 128 samples
     bool pipe_ok = false;  // the lane-pipelined kernel supports this bank
     int n_channels = 0;
     float *zstate = nullptr;
@@ -83,4 +84,5 @@ struct BankPlan {
 void frt_pipe_prepare(BankPlan *pl);
 void frt_pipe_schedule(int n_oct, int logch, long long t_total, int *T /*[BANK_MAX_OCT+1]*/,
                        int *n_steps);
+int frt_pipe_flush_delta(int n_oct, int logch, const int *T);
 cudaError_t frt_pipe_launch(const BankPlan *pl, BankArgs a, int logch, int pack, cudaStream_t st);

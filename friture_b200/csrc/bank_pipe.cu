@@ -118,31 +118,7 @@ __device__ __forceinline__ float lg2_fast(float v) {
     return r;
 }
 
-// what the energy writers need, by value (taking the address of the kernel parameter would move it
-// to local memory)
-struct EmitCtx {
-    float *base;           // energies of this half-warp's first channel, or NULL
-    const float *weight;   // dB offsets or NULL
-    long long ch_stride;   // floats between consecutive channels (n_blocks * nbands)
-    int nbands;
-    int db;
-    int has2;
-};
-
-// friture/octavespectrum.py:119-121: 10*log10(sp + 1e-30) + w
-__device__ __forceinline__ float energy_out(float e, int kband, const EmitCtx &c) {
-    if (!c.db) return e;
-    float v = 3.01029995663981195f * lg2_fast(e + 1e-30f);
-    if (c.weight) v += __ldg(c.weight + kband);
-    return v;
-}
-
-template <class T>
-__device__ __noinline__ void emit(EmitCtx c, float alpha_j, T val, int blk, int kband) {
-    float *o = c.base + (size_t)blk * c.nbands + kband;
-    o[0] = energy_out(alpha_j * v_x(val), kband, c);
-    if (sizeof(T) == 8 && c.has2) o[c.ch_stride] = energy_out(alpha_j * v_y(val), kband, c);
-}
+constexpr int EN_RING = 8;      // blocks of band energies staged in shared memory before the flush
 
 // The two lane groups of a half-warp must run ONE instruction stream with per-lane predicates.
 // Conditions on the (loop-invariant) group index invite the compiler to unswitch the whole
@@ -169,7 +145,7 @@ __device__ __forceinline__ T biquad(T x, T &z1, T &z2, float cc, float na1, floa
 // ruler slot CH-1.  A segment starts at slot s >= CH/2 whenever CH - s is a power of two, and is
 // then segment LOGCH - log2(CH - s).
 __host__ __device__ constexpr int ilog2c(int v) {
-    return v >= 64 ? 6 : v >= 32 ? 5 : v >= 16 ? 4 : v >= 8 ? 3 : v >= 4 ? 2 : v >= 2 ? 1 : 0;
+    return v >= 128 ? 7 : v >= 64 ? 6 : v >= 32 ? 5 : v >= 16 ? 4 : v >= 8 ? 3 : v >= 4 ? 2 : v >= 2 ? 1 : 0;
 }
 __host__ __device__ constexpr bool seg_starts_at(int slot, int ch) {
     return slot >= ch / 2 && ((ch - slot) & (ch - slot - 1)) == 0;
@@ -181,6 +157,16 @@ __host__ __device__ constexpr bool seg_starts_at(int slot, int ch) {
 // input vectors sit in groups 5 (stage 0) and 6 (multiplexed stages), and the second half-warp's
 // slot is displaced by 64 (mod 128) bytes so that the 32-bit accesses of the two halves use
 // different banks.
+// resident one-warp CTAs per SM the register allocation must allow (65536 / (32 * n) registers per
+// thread): the small-step variant serves many channels and wants warps, the large-step variants
+// serve few channels (one warp per scheduler at best) and want registers
+#ifndef PIPE_MINB5
+#define PIPE_MINB5 16
+#endif
+__host__ __device__ constexpr int pipe_min_blocks(int logch, int pack) {
+    return (logch == 5 && pack == 1) ? PIPE_MINB5 : (logch == 6 && pack == 1) ? 12 : 8;
+}
+
 template <int LOGCH, int PACK, int BPO>
 struct PipeLayout {
     static constexpr int CH = 1 << LOGCH;
@@ -196,7 +182,8 @@ struct PipeLayout {
     static constexpr int S = W + 12 * WSTR + 4 * PAD;         // [MAX_OCT][NR][4]: z1A z2A z1B z2B
     static constexpr int ER = S + BANK_MAX_OCT * NR * 4;      // [MAX_OCT][4]: ruler-stage energies
     static constexpr int MB = ER + BANK_MAX_OCT * 4;          // [MAX_OCT + 2][2] mailboxes
-    static constexpr int RAW = MB + (BANK_MAX_OCT + 2) * 2;
+    static constexpr int EN = MB + (BANK_MAX_OCT + 2) * 2;    // [EN_RING][32] staged band energies
+    static constexpr int RAW = EN + EN_RING * 32;
     // round up to 64 (mod 128) bytes
     static constexpr int RAWB = RAW * TB;
     static constexpr int TOTALB = ((RAWB + 63) / 128) * 128 + 64;
@@ -205,7 +192,7 @@ struct PipeLayout {
 };
 
 template <int LOGCH, int PACK, int BPO>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32, pipe_min_blocks(LOGCH, PACK))
 bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
     using T = typename VT<PACK>::t;
     using LY = PipeLayout<LOGCH, PACK, BPO>;
@@ -215,7 +202,7 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
     constexpr int GB = (PACK == 1 ? 32 : 16) / 4;   // groups whose inputs are loaded ahead
     constexpr int RX = PIPE_RX, PF = PIPE_PF;
     static_assert(2 * NR <= 16, "two lane groups must fit in a half-warp");
-    static_assert(LOGCH == 5 || LOGCH == 6, "steps of 32 or 64 samples");
+    static_assert(LOGCH >= 5 && LOGCH <= 7, "steps of 32, 64 or 128 samples");
     static_assert(NG % GB == 0, "whole load batches");
 
     extern __shared__ __align__(128) float4 smem4[];
@@ -224,7 +211,8 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
     T *sm = reinterpret_cast<T *>(smem4) + h * LY::TOTAL;       // this half-warp's channel slot
     int *sT = reinterpret_cast<int *>(reinterpret_cast<T *>(smem4) + 2 * LY::TOTAL);   // [MAX_OCT + 2]
     float *sAl = reinterpret_cast<float *>(sT + 12);            // [MAX_OCT + 2]
-    T *sX = sm + LY::X, *sW = sm + LY::W, *sS = sm + LY::S, *sER = sm + LY::ER, *sMB = sm + LY::MB;
+    T *sX = sm + LY::X, *sW = sm + LY::W, *sS = sm + LY::S, *sER = sm + LY::ER, *sMB = sm + LY::MB,
+      *sEN = sm + LY::EN;
 
     // channels of this half-warp (clamped when the last warp is not full; `alive` gates the writes)
     const int cgrp = blockIdx.x * 2 + h;
@@ -239,13 +227,8 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
     const int nbmask = (1 << lognb) - 1;
     const int logblock = lognb + LOGCH;
     const bool want_e = alive && a.energies != nullptr;
-    EmitCtx ectx;
-    ectx.base = a.energies ? a.energies + (size_t)ch0 * a.e_stride : nullptr;
-    ectx.weight = a.db ? a.weight : nullptr;
-    ectx.ch_stride = a.e_stride;
-    ectx.nbands = nbands;
-    ectx.db = a.db;
-    ectx.has2 = has2 ? 1 : 0;
+    float *eout0 = a.energies ? a.energies + (size_t)ch0 * a.e_stride : nullptr;
+    const int fdelta = P.fdelta;
 
     // ---- lane roles (phase A)
     const bool worker = hl < 2 * NR;
@@ -441,8 +424,9 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
                         if (pvR) {
                             sER[jrc * 4 + r] = e;
                             const int bl = logblock - jrc;           // block >> jrc = 2^bl samples
-                            if (want_e && ((m + 1) & ((1 << bl) - 1)) == 0)
-                                emit<T>(ectx, alj * gb_lane * gb_lane, e, ((m + 1) >> bl) - 1, (n_oct - 1 - jrc) * BPO + r);
+                            if (((m + 1) & ((1 << bl) - 1)) == 0)
+                                sEN[((((m + 1) >> bl) - 1) & (EN_RING - 1)) * 32 + (n_oct - 1 - jrc) * BPO + r] =
+                                    v_mul(alj * gb_lane * gb_lane, e);
                         }
                     }
                 }
@@ -494,7 +478,8 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
                     v_set(acc0[b][q], 0.f, 0.f);
                     if (hl + 16 * q == CH - 1) acc0[b][q] = val;
                 }
-                if (hl == 0 && want_e) emit<T>(ectx, P.alpha[0] * P.gband[b] * P.gband[b], val, blk, (n_oct - 1) * BPO + b);
+                if (hl == 0)
+                    sEN[(blk & (EN_RING - 1)) * 32 + (n_oct - 1) * BPO + b] = v_mul(P.alpha[0] * P.gband[b] * P.gband[b], val);
             }
         }
 #pragma unroll
@@ -521,7 +506,8 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
                         v_set(accm[b][q], 0.f, 0.f);
                         if (hl + 16 * q == lo + len - 1) accm[b][q] = val;
                     }
-                    if (hl == 0 && want_e) emit<T>(ectx, sAl[j] * P.gband[b] * P.gband[b], val, blk, kb0 + b);
+                    if (hl == 0)
+                        sEN[(blk & (EN_RING - 1)) * 32 + kb0 + b] = v_mul(sAl[j] * P.gband[b] * P.gband[b], val);
                 }
             } else {
                 // the stage sits in lanes [lo & 15, (lo & 15) + len) of the last register
@@ -540,7 +526,30 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
                     if (mine) {
                         v_set(accm[b][q], 0.f, 0.f);
                         if (hl == l0 + len - 1) accm[b][q] = val;
-                        if (hl == l0 && want_e) emit<T>(ectx, sAl[j] * P.gband[b] * P.gband[b], val, blk, kb0 + b);
+                        if (hl == l0)
+                            sEN[(blk & (EN_RING - 1)) * 32 + kb0 + b] = v_mul(sAl[j] * P.gband[b] * P.gband[b], val);
+                    }
+                }
+            }
+        }
+        // ---- the band vector of the block every stage has reported goes out in one coalesced store
+        {
+            const int kf = k - fdelta + 1;
+            if (kf > 0 && (kf & nbmask) == 0) {
+                __syncwarp();
+                if (want_e) {
+                    const int blk = (kf >> lognb) - 1;
+                    for (int i = hl; i < nbands; i += 16) {
+                        const T v = sEN[(blk & (EN_RING - 1)) * 32 + i];
+                        float e0 = v_x(v), e1 = v_y(v);
+                        if (a.db) {     // friture/octavespectrum.py:119-121: 10*log10(sp + 1e-30) + w
+                            const float w = a.weight ? __ldg(a.weight + i) : 0.f;
+                            e0 = fmaf(3.01029995663981195f, lg2_fast(e0 + 1e-30f), w);
+                            e1 = fmaf(3.01029995663981195f, lg2_fast(e1 + 1e-30f), w);
+                        }
+                        float *o = eout0 + (size_t)blk * nbands + i;
+                        o[0] = e0;
+                        if (PACK == 2 && has2) o[a.e_stride] = e1;
                     }
                 }
             }
@@ -643,14 +652,29 @@ void frt_pipe_schedule(int n_oct, int logch, long long t_total, int *T, int *n_s
         else l = T[j] + (((t_total >> j) - 1) << (j - logch)) + dmax;
         if (l > last) last = l;
     }
+    // block b's band vector is flushed at step (b+1)*NB - 1 + delta
+    const long long flush_last = n_chunks - 1 + frt_pipe_flush_delta(n_oct, logch, T);
+    if (flush_last > last) last = flush_last;
     *n_steps = (int)(last + 1);
+}
+
+// Steps after a block's last stage-0 chunk (step (b+1)*NB - 1) at which every stage has staged the
+// block's band energies: chunked stage j reports T_j steps later, ruler stage j during step
+// T_j - P_j of that scale (readable one phase later, hence + 1).
+int frt_pipe_flush_delta(int n_oct, int logch, const int *T) {
+    int delta = 0;
+    for (int j = 1; j < n_oct; j++) {
+        const int dj = j <= logch ? T[j] : T[j] - (1 << (j - logch)) + 1;
+        if (dj > delta) delta = dj;
+    }
+    return delta;
 }
 
 void frt_pipe_prepare(BankPlan *pl) {
     const BankParams &B = pl->params;
     pl->pipe_ok = (B.bpo == 1 || B.bpo == 3);
     if (!pl->pipe_ok) return;
-    for (int v = 0; v < 2; v++) {
+    for (int v = 0; v < 3; v++) {
         const int logch = 5 + v, CH = 1 << logch;
         PipeParams &P = pl->pipe[v];
         memset(&P, 0, sizeof(P));
@@ -665,6 +689,7 @@ void frt_pipe_prepare(BankPlan *pl) {
         P.gdec = B.gdec;
         for (int j = 0; j <= BANK_MAX_OCT; j++) P.alpha[j] = j < B.n_oct ? (float)pl->alphas[j] : 1.f;
         frt_pipe_schedule(B.n_oct, logch, 0, P.T, nullptr);
+        P.fdelta = frt_pipe_flush_delta(B.n_oct, logch, P.T);
         const double q0 = 1.0 - pl->alphas[0];
         P.aq0 = (float)(1.0 - pow(q0, CH));
         for (int p = 0; p < CH; p++) {
@@ -686,5 +711,6 @@ cudaError_t frt_pipe_launch(const BankPlan *pl, BankArgs a, int logch, int pack,
     int T[BANK_MAX_OCT + 1];
     frt_pipe_schedule(P.n_oct, logch, a.t_total, T, &a.n_steps);
     if (logch == 5) return pack == 2 ? launch_pipe_bpo<5, 2>(P, a, st) : launch_pipe_bpo<5, 1>(P, a, st);
-    return pack == 2 ? launch_pipe_bpo<6, 2>(P, a, st) : launch_pipe_bpo<6, 1>(P, a, st);
+    if (logch == 6) return pack == 2 ? launch_pipe_bpo<6, 2>(P, a, st) : launch_pipe_bpo<6, 1>(P, a, st);
+    return launch_pipe_bpo<7, 1>(P, a, st);
 }

@@ -51,7 +51,16 @@ def n_steps_for(n_oct, logch, t_total, T):
         else:
             m_last = (t_total >> j) - 1
             last = max(last, T[j] + (m_last << (j - logch)) + dmax)
-    return last + 1
+    # block b's band vector leaves the staging ring at step (b+1)*NB - 1 + flush_delta
+    return max(last, n_chunks - 1 + flush_delta(n_oct, logch, T)) + 1
+
+
+def flush_delta(n_oct, logch, T):
+    """Steps after a block's last stage-0 chunk until every stage has staged its band energies."""
+    delta = 0
+    for j in range(1, n_oct):
+        delta = max(delta, T[j] if j <= logch else T[j] - (1 << (j - logch)) + 1)
+    return delta
 
 
 def ctz(v):

@@ -1,8 +1,7 @@
 """Throughput of the filterbank kernels on the GPU box (tuning aid, not the bench):
-python tools/perf_bank.py [channels ...]"""
+python tools/perf_bank.py [channels ...]   (FRT_B200_LIB selects another build of the library)"""
 import os
 import sys
-import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
@@ -27,14 +26,15 @@ def run(C, block, nblk, noct, reps=5):
 
 if __name__ == "__main__":
     chans = [int(v) for v in sys.argv[1:]] or [1024, 2048, 8192]
+    print("library:", os.environ.get("FRT_B200_LIB", "default"))
     for C in chans:
         for block, noct in ((512, 9), (1024, 10)):
             nblk = 256 if block == 512 else 128
             row = []
-            for kern, pack, logch in (("scan", 1, 5), ("pipe", 1, 5), ("pipe", 2, 5), ("pipe", 1, 6), ("pipe", 2, 6)):
+            for kern, pack, logch in (("scan", 1, 5), ("pipe", 1, 5), ("pipe", 2, 5), ("pipe", 1, 6), ("pipe", 1, 7)):
                 os.environ["FRT_BANK_KERNEL"] = kern
                 os.environ["FRT_BANK_PACK"] = str(pack)
                 os.environ["FRT_BANK_LOGCH"] = str(logch)
                 r, ms = run(C, block, nblk, noct)
-                row.append("%s/p%d/c%d %.3g blk/s (%.2f ms)" % (kern, pack, 1 << logch, r, ms))
+                row.append("%s/p%d/c%d %.3g (%.2f ms)" % (kern, pack, 1 << logch, r, ms))
             print("C=%d block=%d noct=%d nblk=%d: %s" % (C, block, noct, nblk, " | ".join(row)), flush=True)
