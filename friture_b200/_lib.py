@@ -67,6 +67,9 @@ SIGNATURES = {
     "frt_bank_state_size": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64)]),
     "frt_bank_get_state": (c_int, [c_void_p, c_void_p, c_void_p]),
     "frt_bank_set_state": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "frt_firbank_plan": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "frt_firbank_reset": (c_int, [c_void_p]),
+    "frt_firbank_process": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p]),
     "frt_gcc_plan": (c_int, [c_void_p, c_int]),
     "frt_gcc_phat": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int,
                              c_void_p, c_void_p, c_void_p]),

@@ -114,6 +114,7 @@ extern "C" int frt_destroy(frt_handle h) {
     frt_gcc_release(h);
     frt_dec_release(h);
     frt_comb_release(h);
+    frt_fir_release(h);
     pipe_release(h);
     delete h;
     return FRT_OK;

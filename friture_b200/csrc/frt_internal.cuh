@@ -45,6 +45,7 @@ struct frt_ctx {
     GccPlan *gcc = nullptr;
     void *dec = nullptr;          // DecPlan (bank.cu)
     void *comb = nullptr;         // CombPipe (combined.cu)
+    void *fir = nullptr;          // FirPlan (bank_fir.cu)
 };
 
 int frt_fail(frt_ctx *h, int code, const char *fmt, ...);
@@ -80,4 +81,5 @@ void frt_bank_release(frt_ctx *h);
 void frt_gcc_release(frt_ctx *h);
 void frt_dec_release(frt_ctx *h);
 void frt_comb_release(frt_ctx *h);
+void frt_fir_release(frt_ctx *h);
 int frt_pipe_ensure(frt_ctx *h, size_t in_bytes, size_t out_bytes);

@@ -54,3 +54,20 @@ def renard(n: int):
     if n not in (10, 20, 40, 80):
         raise ValueError("no Renard series R%d" % n)
     return _R80[::80 // n]
+
+
+_FIR_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "fir.npz")
+_fir_cache = None
+
+
+def fir_taps(bpo: int):
+    """(boct_fir[bpo, 512], bdec_fir[512]): the 512-tap minimum-phase FIR approximations the
+    reference's live filterbank runs by FFT overlap-add (friture/data/generated_fft.npz, loaded at
+    friture/octavefilters.py:123-143); ``tools/make_fir_data.py`` regenerates ``data/fir.npz``."""
+    global _fir_cache
+    if bpo not in SUPPORTED_BPO:
+        raise Exception("Unknown bandsperoctave: %d" % (bpo))
+    if _fir_cache is None:
+        with np.load(_FIR_PATH) as d:
+            _fir_cache = {k: d[k] for k in d.files}
+    return _fir_cache["boct_fir%d" % bpo], _fir_cache["bdec_fir"]

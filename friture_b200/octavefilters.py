@@ -67,7 +67,8 @@ class Octave_Filters():
 
     FIR_LENGTH = FIR_LENGTH
 
-    def __init__(self, bandsperoctave, device=None, n_octaves=NOCTAVE, response_time=1.0, handle=None):
+    def __init__(self, bandsperoctave, device=None, n_octaves=NOCTAVE, response_time=1.0, handle=None,
+                 mode="iir"):
         self.bdec, self.adec, self._sos_dec = filter_data.decimator()
         self.bdec = np.array(self.bdec)
         self.adec = np.array(self.adec)
@@ -77,6 +78,14 @@ class Octave_Filters():
         self._response_time = response_time
         self._plan_key = None
         self._weighting = None
+        # "iir": the reference's IIR designs themselves (the bank its own tests check against,
+        # friture/filter.py:86-118) -- fused energies, the throughput path.  "fft": the numerics of
+        # the reference's live filter(), 512-tap FIR approximations run by FFT overlap-add
+        # (friture/filter.py:136-247), computed as exact FIR convolutions; band outputs only.
+        if mode not in ("iir", "fft"):
+            raise ValueError("mode must be 'iir' or 'fft'")
+        self._mode = mode
+        self._fir_key = None
         self.setbandsperoctave(bandsperoctave)
 
     # ------------------------------------------------------------------ reference surface
@@ -90,6 +99,9 @@ class Octave_Filters():
             raise Exception("Filter input is too small")   # friture/signal/decimate.py:33-34
         import torch
         dev = self._torch_device()
+        if self._mode == "fft" and x.shape[0] > 4096:
+            raise ValueError("fft mode: at most 4096 samples per call (the reference's live path is "
+                             "valid up to 1024, friture/filter_design.py:400-401)")
         y, _ = self.filter_batch(torch.from_numpy(x).to(dev)[None, :], block=x.shape[0],
                                  energies=False, want_y=True)
         ylist = [v[0].cpu().numpy().astype(np.float64) for v in y]
@@ -115,6 +127,7 @@ class Octave_Filters():
         self.A, self.B, self.C = abc_weighting(self.fi)     # friture/octavefilters.py:76-82
         self._weighting = None
         self._plan_key = None   # new filters -> state restarts from zero (octavefilters.py:151-158)
+        self._fir_key = None
         self.f_nominal = self._nominal_labels()
 
     def _nominal_labels(self):
@@ -169,6 +182,40 @@ class Octave_Filters():
     def reset(self):
         if self._plan_key is not None:
             self.handle.call("frt_bank_reset")
+        if self._fir_key is not None:
+            self.handle.call("frt_firbank_reset")
+
+    def _ensure_fir_plan(self, n_channels):
+        key = (n_channels, self.bandsperoctave, self._n_octaves)
+        if key == self._fir_key:
+            return
+        boct_fir, bdec_fir = filter_data.fir_taps(self.bandsperoctave)
+        boct_fir = np.ascontiguousarray(boct_fir, dtype=np.float64)
+        bdec_fir = np.ascontiguousarray(bdec_fir, dtype=np.float64)
+        self.handle.call("frt_firbank_plan", int(n_channels), int(self.bandsperoctave), int(self._n_octaves),
+                         int(boct_fir.shape[1]), _lib._ptr(boct_fir), _lib._ptr(bdec_fir))
+        self._fir_key = key
+
+    def _filter_batch_fir(self, x, block, stream=None):
+        """Live-path numerics: band outputs of x [C, n_blocks*block], block by block."""
+        import torch
+        C, T = x.shape
+        if block > 4096 or block % (1 << (self._n_octaves - 1)):
+            raise ValueError("fft mode: block must be a multiple of %d and at most 4096"
+                             % (1 << (self._n_octaves - 1)))
+        self._ensure_fir_plan(C)
+        offsets, lengths = ragged_layout(block, self.bandsperoctave, self._n_octaves)
+        ystride = int(offsets[-1] + lengths[-1])
+        sp = _lib.current_stream_ptr(x.device) if stream is None else c_void_p(int(stream))
+        parts = []
+        for b in range(T // block):
+            ybuf = torch.empty((C, ystride), dtype=torch.float32, device=x.device)
+            xb = x[:, b * block:(b + 1) * block]
+            self.handle.call("frt_firbank_process", _lib._ptr(xb), int(x.stride(0)) if C > 1 else int(T),
+                             int(block), _lib._ptr(ybuf), ystride, sp)
+            parts.append(ybuf)
+        return [torch.cat([p[:, int(o):int(o) + int(n)] for p in parts], dim=1)
+                for o, n in zip(offsets, lengths)]
 
     def set_weighting(self, weighting):
         """dB offsets added to the dB energies (``db=True``), as the octave widget does
@@ -229,6 +276,10 @@ class Octave_Filters():
                              "block (exp_smoothing.py:43-47)" % MAX_BLOCK)
         self.handle.check_device(x)
         n_blocks = T // block
+        if self._mode == "fft":
+            if energies:
+                raise ValueError("fft mode gives the band outputs only (energies=False, want_y=True)")
+            return self._filter_batch_fir(x, block, stream), None
         self._ensure_plan(C)
         e = None
         if energies:

@@ -129,6 +129,20 @@ int frt_bank_state_size(frt_handle h, int64_t *z_floats, int64_t *ema_floats);
 int frt_bank_get_state(frt_handle h, float *z_host, float *ema_host);
 int frt_bank_set_state(frt_handle h, const float *z_host, const float *ema_host);
 
+/* ---------------------------------------------------------------- live-path filterbank (FIR)
+ * The numerics of the reference's LIVE `Octave_Filters.filter` (friture/octavefilters.py:49-58):
+ * FFT overlap-add with 512-tap minimum-phase FIR approximations of the same designs
+ * (friture/filter.py:136-247, taps friture/data/generated_fft.npz).  Overlap-add is an exact linear
+ * convolution, which the kernel computes directly (double accumulation), carrying the last
+ * n_taps-1 inputs of every stage.  Parity mode; the IIR bank above is the throughput path.
+ *   fir_band [bands_per_octave][n_taps], fir_dec [n_taps]  (float64 taps)
+ *   process: n_samples <= 4096 and a multiple of 2^(n_octaves-1); y_dev ragged as in frt_bank_process */
+int frt_firbank_plan(frt_handle h, int n_channels, int bands_per_octave, int n_octaves, int n_taps,
+                     const double *fir_band, const double *fir_dec);
+int frt_firbank_reset(frt_handle h);
+int frt_firbank_process(frt_handle h, const float *x_dev, int64_t x_stride, int n_samples,
+                        float *y_dev, int64_t y_stride, void *stream);
+
 /* ---------------------------------------------------------------- combined per-hop analysis
  * What Spectrogram_Widget.handle_new_data (friture/spectrogram.py:131-169) and
  * OctaveSpectrum_Widget.handle_new_data (friture/octavespectrum.py:91-121) compute from the same

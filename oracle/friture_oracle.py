@@ -197,6 +197,99 @@ def octave_frequencies(total_bands_count, bands_per_octave):
     return fi, fi * np.sqrt(2 ** (-b)), fi * np.sqrt(2 ** b)
 
 
+# --------------------------------------------------------------------------- live FFT-OLA bank
+FIR_LENGTH = 512           # friture/octavefilters.py:35
+
+
+def fft_bank_sizes(fir_length=FIR_LENGTH, noctave=NOCTAVE, max_block=1024):
+    """Per-stage FFT sizes of the live bank: the next 2^a 3^b 5^c >= N_stage + fir_length - 1 with
+    N_stage = max_block / 2^j (friture/filter_design.py:400-401 committed as
+    friture/data/generated_fft.npz `*_fft_sizes` = [1536, 1024, 768, 640, 576, 576, 540, 540, 540])."""
+    def next_composite(n):
+        while True:
+            m = n
+            for p in (2, 3, 5):
+                while m % p == 0:
+                    m //= p
+            if m == 1:
+                return n
+            n += 1
+    return [next_composite((max_block >> j) + fir_length - 1) for j in range(noctave)]
+
+
+def fft_bank_state(bpo, fir_length=FIR_LENGTH, noctave=NOCTAVE):
+    """Zero overlap buffers (friture/octavefilters.py:145-158)."""
+    return ([np.zeros((bpo, fir_length - 1)) for _ in range(noctave)],
+            [np.zeros(fir_length - 1) for _ in range(noctave)])
+
+
+def octave_filter_bank_decimation_fft(boct_fir, bdec_fir, x, overlaps_oct, overlaps_dec,
+                                      noctave=NOCTAVE, fft_sizes=None):
+    """The reference's live filterbank (friture/filter.py:136-247): per stage one shared rfft of
+    the stage input, multiplication with the rfft of the 512-tap FIRs, irfft, pending overlap tail
+    added element-wise (fixed fir_length-1 buffer), first N_s samples out, decimator output
+    [:N_s:2] to the next stage.  Returns (y, dec, overlaps_oct, overlaps_dec) like the reference."""
+    boct_fir = np.asarray(boct_fir, dtype=np.float64)
+    bdec_fir = np.asarray(bdec_fir, dtype=np.float64)
+    bpo, L = boct_fir.shape
+    Lm1 = L - 1
+    if fft_sizes is None:
+        fft_sizes = fft_bank_sizes(L, noctave)
+    nb = noctave * bpo
+    y = [None] * nb
+    dec = [0] * nb
+    k = nb - 1
+    x_dec = np.asarray(x, dtype=np.float64)
+    ov_o, ov_d = [], []
+    for j in range(noctave):
+        N_s = len(x_dec)
+        n = fft_sizes[j]
+        X = np.fft.rfft(x_dec, n)
+        y_oct = np.fft.irfft(X[None, :] * np.fft.rfft(boct_fir, n, axis=1), n, axis=1)
+        y_dec = np.fft.irfft(X * np.fft.rfft(bdec_fir, n), n)
+        pend, pend_d = overlaps_oct[j], overlaps_dec[j]
+        add = min(pend.shape[1], N_s)
+        y_oct[:, :add] += pend[:, :add]
+        y_dec[:add] += pend_d[:add]
+        for i in range(bpo)[::-1]:
+            y[k] = y_oct[i, :N_s]
+            dec[k] = 2 ** j
+            k -= 1
+        x_dec = y_dec[:N_s:2]
+        tail = y_oct[:, N_s:N_s + Lm1].copy()
+        rest = pend[:, add:]
+        tail[:, :rest.shape[1]] += rest
+        ov_o.append(tail)
+        tail_d = y_dec[N_s:N_s + Lm1].copy()
+        rest_d = pend_d[add:]
+        tail_d[:len(rest_d)] += rest_d
+        ov_d.append(tail_d)
+    return y, dec, ov_o, ov_d
+
+
+def fir_bank_direct(boct_fir, bdec_fir, x, hist, noctave=NOCTAVE):
+    """The same filterbank as plain FIR convolutions with carried input history (what the GPU
+    kernel computes): y_i = conv(x_j, h_i), x_{j+1} = conv(x_j, h_dec)[::2].  hist[j] holds the
+    last L-1 inputs of stage j.  Equal to the overlap-add form up to rounding."""
+    boct_fir = np.asarray(boct_fir, dtype=np.float64)
+    bpo, L = boct_fir.shape
+    nb = noctave * bpo
+    y = [None] * nb
+    k = nb - 1
+    x_dec = np.asarray(x, dtype=np.float64)
+    new_hist = []
+    for j in range(noctave):
+        N_s = len(x_dec)
+        ext = np.concatenate([hist[j], x_dec])
+        for i in range(bpo)[::-1]:
+            y[k] = np.convolve(ext, boct_fir[i])[L - 1:L - 1 + N_s]
+            k -= 1
+        yd = np.convolve(ext, bdec_fir)[L - 1:L - 1 + N_s]
+        new_hist.append(ext[-(L - 1):])
+        x_dec = yd[::2]
+    return y, new_hist
+
+
 # --------------------------------------------------------------------------- smoothing
 def smoothing_alpha(response_time, rate):
     """alpha so that the newest n = T*rate samples carry 65 % of the weight:

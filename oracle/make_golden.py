@@ -122,6 +122,28 @@ def main():
     d["f_nominal_bpo3"] = np.array(of.f_nominal)
     np.savez_compressed(os.path.join(OUT, "octave_bank.npz"), **d)
 
+    # (iv-b) band outputs of the LIVE path itself (parity target of Octave_Filters(mode="fft"))
+    out = {}
+    for bpo in (3, 12):
+        of = ref.octavefilters.Octave_Filters(bpo)
+        ys = [[] for _ in range(NOCTAVE * bpo)]
+        for b in range(16):
+            y, dec = of.filter(xs[b * 512:(b + 1) * 512].astype(np.float64))
+            for k in range(NOCTAVE * bpo):
+                ys[k].append(y[k])
+        for k in (0, NOCTAVE * bpo // 2, NOCTAVE * bpo - 1):
+            out["y_bpo%d_band%d" % (bpo, k)] = np.concatenate(ys[k])
+        out["energy_sum_bpo%d" % bpo] = np.array([np.sum(np.concatenate(v) ** 2) for v in ys])
+        out["dec_bpo%d" % bpo] = np.array(dec)
+    of = ref.octavefilters.Octave_Filters(3)
+    ys = [[] for _ in range(27)]
+    for b in range(8):
+        y, _ = of.filter(xs[b * 1024:(b + 1) * 1024].astype(np.float64))
+        for k in range(27):
+            ys[k].append(y[k])
+    out["energy_sum_bpo3_block1024"] = np.array([np.sum(np.concatenate(v) ** 2) for v in ys])
+    np.savez_compressed(os.path.join(OUT, "octave_bank_fft.npz"), **out)
+
     # (v) GCC-PHAT, L = 24000 with a known integer delay
     L = 24000
     rng = np.random.default_rng(404)

@@ -104,3 +104,28 @@ def test_shim_labels_and_attributes_match_reference(ref):
         pm.set_fftsize(n)
         for name in ("window", "freq", "A", "B", "C", "size_sq", "fft_size"):
             assert np.array_equal(getattr(pm, name), getattr(pr, name)), name
+
+
+def test_live_fft_bank_restatement_and_fir_data(ref):
+    """oracle.octave_filter_bank_decimation_fft == the unmodified reference's Octave_Filters.filter
+    (live FFT overlap-add path, friture/filter.py:136-247) to 1e-15; the direct FIR form the GPU
+    kernel computes equals it to rounding; data/fir.npz holds the reference's taps."""
+    from friture_b200 import filter_data
+    from oracle import friture_oracle as fo
+    assert fo.fft_bank_sizes() == [1536, 1024, 768, 640, 576, 576, 540, 540, 540]
+    rng = np.random.default_rng(1)
+    for bpo in (1, 3, 24):
+        boct_fir, bdec_fir = filter_data.fir_taps(bpo)
+        of = ref.octavefilters.Octave_Filters(bpo)
+        assert np.array_equal(np.stack(of._boct_fir), boct_fir) and np.array_equal(of._bdec_fir, bdec_fir)
+        oo, od = fo.fft_bank_state(bpo)
+        hist = [np.zeros(511) for _ in range(9)]
+        for blk in range(5):
+            x = rng.standard_normal(512 if blk % 2 else 1024) * 0.1
+            yr, decr = of.filter(x)
+            y, dec, oo, od = fo.octave_filter_bank_decimation_fft(boct_fir, bdec_fir, x, oo, od)
+            y2, hist = fo.fir_bank_direct(boct_fir, bdec_fir, x, hist)
+            assert dec == decr
+            for a, b, c in zip(y, yr, y2):
+                assert np.max(np.abs(a - b)) < 1e-14
+                assert np.max(np.abs(c - b)) < 1e-12 * max(np.max(np.abs(b)), 1.0)
