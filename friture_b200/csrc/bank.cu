@@ -657,7 +657,7 @@ extern "C" int frt_bank_set_weighting(frt_handle h, const float *weight_db_host)
 
 extern "C" int frt_bank_schedule(int n_octaves, int log2_chunk, int64_t n_samples, int *stage_start,
                                  int *n_steps) {
-    if (n_octaves < 1 || n_octaves > MAX_OCT || (log2_chunk < 5 || log2_chunk > 7) || !stage_start ||
+    if (n_octaves < 1 || n_octaves > MAX_OCT || (log2_chunk != 5 && log2_chunk != 6) || !stage_start ||
         n_samples < 0)
         return FRT_EINVAL;
     int T[BANK_MAX_OCT + 1];
@@ -825,16 +825,16 @@ static int bank_process_impl(frt_handle h, const float *x_dev, int64_t x_stride,
     bool use_pipe = pl->pipe_ok && !y_dev && pow2 && (block >> (P.n_oct - 1)) >= 1;
     if (force_k && force_k[0] == 's') use_pipe = false;
     if (use_pipe) {
-        // measured on B200 (blocks/s of 512 samples, 27 bands): 1024 channels 5.2e7 / 6.8e7 with 32- /
-        // 64-sample steps, 8192 channels 1.31e8 / 1.10e8; packing two channels per lane (FFMA2) halves
-        // the warps and never paid.  The choice depends on the plan and the block length only, so a
-        // stream gives the same bits however it is cut into launches.
-        int pack = 1;
+        // measured on B200 (blocks/s of 512 samples, 27 bands; steps of 32 / 64 samples, one / two
+        // channels per lane): 1024 channels 6.1e7 (32) / 8.7e7 (64); 2048: 9.9e7 / 1.35e8; 4096: 1.04e8 /
+        // 1.33e8 / 1.44e8 (32, two per lane); 8192: 1.29e8 / 1.34e8 / 1.44e8.  128-sample steps brought
+        // nothing over 64.  The choice depends on the plan and the block length only, so a stream
+        // gives the same bits however it is cut into launches.
+        int pack = pl->n_channels > 3072 ? 2 : 1;
         int logch = (block >= 512 && pl->n_channels <= 3072) ? 6 : 5;
         if (force_p) pack = force_p[0] == '2' ? 2 : 1;
-        if (force_c) logch = force_c[0] == '7' ? 7 : (force_c[0] == '6' ? 6 : 5);
+        if (force_c) logch = force_c[0] == '6' ? 6 : 5;
         while (logch > 5 && block < (4 << logch)) logch--;
-        if (logch == 7) pack = 1;
         e = frt_pipe_launch(pl, a, logch, pack, st);
     } else if (tile == 1024) e = launch_bank<32>(pl, a, st);
     else if (tile == 512) e = launch_bank<16>(pl, a, st);

@@ -70,7 +70,7 @@ struct BankArgs {
 
 struct BankPlan {
     BankParams params;
-    PipeParams pipe[3];    // steps of 32, 64, 128 samples
+    PipeParams pipe[2];    // [0]: 32-sample steps, [1]: 64-sample steps
     bool pipe_ok = false;  // the lane-pipelined kernel supports this bank
     int n_channels = 0;
     float *zstate = nullptr;

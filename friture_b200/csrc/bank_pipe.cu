@@ -202,7 +202,7 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
     constexpr int GB = (PACK == 1 ? 32 : 16) / 4;   // groups whose inputs are loaded ahead
     constexpr int RX = PIPE_RX, PF = PIPE_PF;
     static_assert(2 * NR <= 16, "two lane groups must fit in a half-warp");
-    static_assert(LOGCH >= 5 && LOGCH <= 7, "steps of 32, 64 or 128 samples");
+    static_assert(LOGCH == 5 || LOGCH == 6, "steps of 32 or 64 samples");
     static_assert(NG % GB == 0, "whole load batches");
 
     extern __shared__ __align__(128) float4 smem4[];
@@ -674,7 +674,7 @@ void frt_pipe_prepare(BankPlan *pl) {
     const BankParams &B = pl->params;
     pl->pipe_ok = (B.bpo == 1 || B.bpo == 3);
     if (!pl->pipe_ok) return;
-    for (int v = 0; v < 3; v++) {
+    for (int v = 0; v < 2; v++) {
         const int logch = 5 + v, CH = 1 << logch;
         PipeParams &P = pl->pipe[v];
         memset(&P, 0, sizeof(P));
@@ -711,6 +711,5 @@ cudaError_t frt_pipe_launch(const BankPlan *pl, BankArgs a, int logch, int pack,
     int T[BANK_MAX_OCT + 1];
     frt_pipe_schedule(P.n_oct, logch, a.t_total, T, &a.n_steps);
     if (logch == 5) return pack == 2 ? launch_pipe_bpo<5, 2>(P, a, st) : launch_pipe_bpo<5, 1>(P, a, st);
-    if (logch == 6) return pack == 2 ? launch_pipe_bpo<6, 2>(P, a, st) : launch_pipe_bpo<6, 1>(P, a, st);
-    return launch_pipe_bpo<7, 1>(P, a, st);
+    return pack == 2 ? launch_pipe_bpo<6, 2>(P, a, st) : launch_pipe_bpo<6, 1>(P, a, st);
 }

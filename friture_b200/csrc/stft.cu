@@ -452,39 +452,17 @@ stft_multi_kernel(const float *__restrict__ x, long long x_stride, long long n_f
         const long long f = item - c * n_frames;
         const float *p = x + c * x_stride + f * hop;
         float2 v[32];
-        if (vec_ok == 2) {
-            // 16-byte aligned frames: the CTA stages the frame cooperatively with coalesced 128-bit
-            // loads (thread tid takes float4 #(tid + 32 R i) = complex values 2m, 2m+1), applies the
-            // window and drops every value into the tile of the warp that owns it (z[idx] belongs to
-            // sub-sequence idx % R at position idx / R); each warp then reads its 1024 values
-            // conflict-free.  The strided gather below fetched every 32-byte sector R times.
-            const float4 *p4 = reinterpret_cast<const float4 *>(p);
-            const float4 *w4 = reinterpret_cast<const float4 *>(win2);
-#pragma unroll 4
-            for (int i = 0; i < 16; i++) {          // N/4 float4 per frame over 32 R threads
-                const int m = tid + 32 * R * i;
-                const float4 xv = __ldg(p4 + m), wv = __ldg(w4 + m);
-                const int i0 = 2 * m, i1 = 2 * m + 1;
-                s_tiles[(i0 % R) * FAST_TILE + i0 / R] = make_float2(xv.x * wv.x, xv.y * wv.y);
-                s_tiles[(i1 % R) * FAST_TILE + i1 / R] = make_float2(xv.z * wv.z, xv.w * wv.w);
-            }
-            __syncthreads();
 #pragma unroll
-            for (int n1 = 0; n1 < 32; n1++) v[n1] = s_x[32 * n1 + lane];
-            __syncwarp();
-        } else {
-#pragma unroll
-            for (int n1 = 0; n1 < 32; n1++) {
-                const int idx = R * (32 * n1 + lane) + warp;      // z[idx] = x[2 idx] + j x[2 idx + 1]
-                float2 xv;
-                if (vec_ok) {
-                    xv = __ldg(reinterpret_cast<const float2 *>(p) + idx);
-                } else {
-                    xv.x = __ldg(p + 2 * idx);
-                    xv.y = __ldg(p + 2 * idx + 1);
-                }
-                v[n1] = __fmul2_rn(xv, __ldg(win2 + idx));
+        for (int n1 = 0; n1 < 32; n1++) {
+            const int idx = R * (32 * n1 + lane) + warp;      // z[idx] = x[2 idx] + j x[2 idx + 1]
+            float2 xv;
+            if (vec_ok) {
+                xv = __ldg(reinterpret_cast<const float2 *>(p) + idx);
+            } else {
+                xv.x = __ldg(p + 2 * idx);
+                xv.y = __ldg(p + 2 * idx + 1);
             }
+            v[n1] = __fmul2_rn(xv, __ldg(win2 + idx));
         }
         dft32(v);
 #pragma unroll

@@ -13,7 +13,7 @@ from test_bank_gpu import energy_rel_err, make_x, oracle_run  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = [(1, 5), (2, 5), (1, 6), (2, 6), (1, 7)]
+VARIANTS = [(1, 5), (2, 5), (1, 6), (2, 6)]
 
 
 @pytest.fixture

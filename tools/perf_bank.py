@@ -31,7 +31,7 @@ if __name__ == "__main__":
         for block, noct in ((512, 9), (1024, 10)):
             nblk = 256 if block == 512 else 128
             row = []
-            for kern, pack, logch in (("scan", 1, 5), ("pipe", 1, 5), ("pipe", 2, 5), ("pipe", 1, 6), ("pipe", 1, 7)):
+            for kern, pack, logch in (("scan", 1, 5), ("pipe", 1, 5), ("pipe", 2, 5), ("pipe", 1, 6), ("pipe", 2, 6)):
                 os.environ["FRT_BANK_KERNEL"] = kern
                 os.environ["FRT_BANK_PACK"] = str(pack)
                 os.environ["FRT_BANK_LOGCH"] = str(logch)
