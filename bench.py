@@ -412,7 +412,7 @@ class Combined:
     """configs[4]'s unit: STFT column + 30-band vector per channel-hop; at world > 1 the columns are
     all-gathered inside the step (chunked, overlapped)."""
     name = "combined"
-    kernel = "bank_pipe_kernel (filterbank) -- ~90% of the step; stft2048_kernel overlaps on a second stream"
+    kernel = "bank_pipe_kernel (filterbank) -- ~90% of the step; stft2048_kernel runs behind it"
 
     def __init__(self, C, F, dev, rank, world, gather=True, n_oct=N_OCT):
         import torch
@@ -442,13 +442,11 @@ class Combined:
             self.an.process_sharded(self.x, self.gathered, self.spec_chunks, self.bands, self.n_chunks)
             return
         if timed:     # the dominant kernel's own duration, on the stream it runs on
-            s_bank = self.an._side_streams()[1]
             e0, e1 = event_pair()
-            cur = torch.cuda.current_stream(self.dev)
-            s_bank.wait_stream(cur)
-            e0.record(s_bank)
-            self.an.process(self.x, self.spec, self.bands)
-            e1.record(s_bank)
+            self.an.proc.stft(self.x, hop=HOP, log=True, out=self.spec)
+            e0.record()
+            self.an._bank(self.x, self.bands)
+            e1.record()
             self.bank_events.append((e0, e1))
         else:
             self.an.process(self.x, self.spec, self.bands)

@@ -23,7 +23,8 @@ import numpy as np
 TOL = 1e-5        # relative error of the log-power / band-energy vector
 FLOOR_DB = 50.0   # below ~this far under the frame mean power float32 cannot resolve 1e-3 dB
 AMP_TOL = 5e-6    # amplitude noise allowance for deep nulls, relative to the frame rms
-STRICT_MAX_BINS = 200000   # strict every-bin criterion up to this sample size
+STRICT_MAX_BINS = 65536    # strict every-bin criterion up to this sample size (expected number of
+                           # float32-unresolvable nulls, ~3e-6 per bin, stays below 0.2)
 
 
 def rel_err(got, ref):
@@ -34,7 +35,7 @@ def rel_err(got, ref):
     return float(np.max(np.abs(got - ref)) / max(np.max(np.abs(ref)), 1.0))
 
 
-def logpower_errors(got_db, ref_db, eps=1e-30):
+def logpower_errors(got_db, ref_db, eps=1e-30, floor_db=None):
     """got_db, ref_db: [..., bins] log-power (10*log10(P+eps)).  Returns a dict with
     rel_above_floor (vector-relative error over bins >= mean-FLOOR_DB), amp_err (worst
     amplitude error over ALL bins, relative to the frame rms), rel_all, frac_above_floor."""
@@ -42,7 +43,7 @@ def logpower_errors(got_db, ref_db, eps=1e-30):
     ref_db = np.asarray(ref_db, dtype=np.float64)
     p_ref = np.maximum(10.0 ** (ref_db / 10.0) - eps, 0.0)
     mean_p = np.mean(p_ref, axis=-1, keepdims=True)
-    floor_db = 10.0 * np.log10(mean_p + eps) - FLOOR_DB
+    floor_db = 10.0 * np.log10(mean_p + eps) - (FLOOR_DB if floor_db is None else floor_db)
     mask = ref_db >= floor_db
     denom = max(float(np.max(np.abs(ref_db))), 1.0) if ref_db.size else 1.0
     diff = np.abs(got_db - ref_db)
@@ -67,11 +68,12 @@ def logpower_ok(e, min_frac=0.9999, strict=False):
     return ok
 
 
-def assert_logpower_parity(got_db, ref_db, min_frac=0.9999, strict=None):
+def assert_logpower_parity(got_db, ref_db, min_frac=0.9999, strict=None, floor_db=None):
     """Broadband inputs: strict every-bin criterion up to STRICT_MAX_BINS bins (strict=None picks
     that), and (almost) every bin above the floor.  Tonal inputs, whose mean power is dominated by
-    a few bins, pass min_frac=0 and strict=False."""
-    e = logpower_errors(got_db, ref_db)
+    a few bins, pass min_frac=0, strict=False and floor_db=40 (the frame mean is the tone there: the
+    float32 noise floor sits only ~45 dB below it)."""
+    e = logpower_errors(got_db, ref_db, floor_db=floor_db)
     if strict is None:
         strict = np.asarray(ref_db).size <= STRICT_MAX_BINS and min_frac > 0
     assert logpower_ok(e, min_frac, strict), e

@@ -51,12 +51,15 @@ def test_config3_full_size_scaling_and_permutation():
     e3 = Octave_Filters(3).energies_batch(x[perm].contiguous(), block=B)
     assert torch.equal(e3, e1[perm])
     assert bool(torch.isfinite(e1).all()) and float(e1.min()) >= 0.0
-    # many channels take the one-warp-per-channel kernel, few the three-warp one: same numbers
+    # a channel's numbers do not depend on its neighbours (same kernel variant: same bits) ...
     e4 = Octave_Filters(3).energies_batch(x[:8].contiguous(), block=B)
     assert torch.equal(e4, e1[:8])
+    # ... and at 8192 channels, where the dispatcher picks 32-sample steps with two channels per
+    # lane, only the rounding of the smoothing sums differs
     big = torch.cat([x[:8]] * 1024, dim=0)[:8192, :B * 4].contiguous()
     e5 = Octave_Filters(3).energies_batch(big, block=B)
-    assert torch.equal(e5[:8], e1[:8, :4])
+    ref = e1[:8, :4]
+    assert float(((e5[:8] - ref).abs() / ref.abs().amax(-1, keepdim=True)).max()) < 2e-6
 
 
 def test_config4_full_size_delays():
