@@ -346,7 +346,7 @@ def workload_config(args, world):
             "n_fft": N_FFT, "hop": HOP, "channels_per_gpu": args.channels,
             "hops_per_channel": args.frames, "global_channels": args.channels * world,
             "parallelism": ("channel-sharded x%d" % world) +
-                           (", final NCCL all-gather of the spectrogram columns inside the timed region, "
+                           (", final all-gather of the spectrogram columns over NVLink inside the timed region, "
                             "overlapped with the filterbank" if world > 1 and args.workload == "combined"
                             else ", no data-path collective"),
             "l2_policy": "inputs and outputs of a step (%.2f GB/GPU) are larger than L2; no flush needed"
@@ -414,7 +414,7 @@ class Combined:
     name = "combined"
     kernel = "bank_pipe_kernel (filterbank) -- ~90% of the step; stft2048_kernel runs behind it"
 
-    def __init__(self, C, F, dev, rank, world, gather=True, n_oct=N_OCT):
+    def __init__(self, C, F, dev, rank, world, gather=True, n_oct=N_OCT, transport="peer"):
         import torch
         from friture_b200.analyzer import ChannelAnalyzer
         self.C, self.F, self.dev, self.world = C, F, dev, world
@@ -425,21 +425,26 @@ class Combined:
         self.bands = torch.empty((C, F + 1, 3 * n_oct), dtype=torch.float32, device=dev)
         self.gather = gather and world > 1
         self.n_chunks = 8 if F % 8 == 0 else 1
+        self.transport = transport
         if self.gather:
             fc = F // self.n_chunks
-            self.spec_chunks = torch.empty((self.n_chunks, C, fc, NBINS), dtype=torch.float32, device=dev)
-            self.gathered = torch.empty((self.n_chunks, world * C, fc, NBINS), dtype=torch.float32, device=dev)
+            self.spec_chunks = self.gathered = None
+            if transport == "nccl":
+                self.spec_chunks = torch.empty((self.n_chunks, C, fc, NBINS), dtype=torch.float32, device=dev)
+                self.gathered = torch.empty((self.n_chunks, world * C, fc, NBINS), dtype=torch.float32, device=dev)
             self.spec = None
         else:
             self.spec = torch.empty((C, F, NBINS), dtype=torch.float32, device=dev)
         self.units = C * F
+        # our kernels per step (the copy-engine pushes / NCCL kernels are not ours)
         self.launches_per_step = (1 + self.n_chunks) if self.gather else 2
         self.bank_events = []
 
     def step(self, timed=False):
         import torch
         if self.gather:
-            self.an.process_sharded(self.x, self.gathered, self.spec_chunks, self.bands, self.n_chunks)
+            self.spec_chunks, _, self.gathered = self.an.process_sharded(
+                self.x, self.gathered, self.spec_chunks, self.bands, self.n_chunks, transport=self.transport)
             return
         if timed:     # the dominant kernel's own duration, on the stream it runs on
             e0, e1 = event_pair()
@@ -480,6 +485,18 @@ class Combined:
         res = {"logpower_rel": strict_rel(got_spec, ref_spec), "band_db_rel": strict_rel(got_b, ref_b),
                "criterion": "max|got-ref| / max(max|ref|, 1) < 1e-5 on %d ch x %d hops" % (cs, fs)}
         res["ok"] = res["logpower_rel"] < 1e-5 and res["band_db_rel"] < 1e-5
+        if self.gather:
+            # the collective: every rank's block of the gathered array equals what that rank computed
+            import torch.distributed as dist
+            if self.transport == "peer":
+                self.an.peer_gather.wait_all()
+            g = self.gathered.reshape(self.n_chunks, self.world, self.C, -1)
+            mine = float(g[0, dist.get_rank(), 0].double().sum().item())
+            sums = [None] * self.world
+            dist.all_gather_object(sums, mine)
+            got = [float(g[0, r, 0].double().sum().item()) for r in range(self.world)]
+            res["gathered_blocks_match"] = bool(all(a == b for a, b in zip(got, sums)))
+            res["ok"] = res["ok"] and res["gathered_blocks_match"]
         self.an.bank.reset()
         return res
 
@@ -797,6 +814,9 @@ def other_workloads(args, dev, rank, world, barrier, peak, peak_src):
         # reduction (one smoothed column per channel and tick instead of one per frame)
         res["combined_no_gather"] = quick(Combined, args.channels, args.frames, dev, rank, world, barrier, peak,
                                           peak_src, reps=5, gather=False)
+        other = "nccl" if args.transport == "peer" else "peer"
+        res["combined_gather_via_%s" % other] = quick(Combined, args.channels, args.frames, dev, rank, world, barrier,
+                                                      peak, peak_src, reps=5, transport=other)
         from friture_b200.spectrum import SpectrumAnalyzer
         from friture_b200.sharded import allgather_channels
         C, F = args.channels, args.frames
@@ -860,6 +880,8 @@ def main():
     ap.add_argument("--frames", type=int, default=None, help="hops / frames / blocks per channel per step")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-gather", action="store_true", help="N > 1: leave the all-gather out of the step")
+    ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: copy-engine pushes over NVLink peer memory (default) or NCCL all-gather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-others", action="store_true")
@@ -895,7 +917,8 @@ def main():
         torch.cuda.synchronize()
 
     from friture_b200 import _lib
-    wl = WORKLOADS[args.workload](args.channels, args.frames, dev, rank, world, gather=not args.no_gather)
+    wl = WORKLOADS[args.workload](args.channels, args.frames, dev, rank, world, gather=not args.no_gather,
+                                  transport=args.transport)
     perr = wl.parity()
     if not perr.get("ok"):
         raise SystemExit("bench.py: parity gate failed: %r" % (perr,))
@@ -928,7 +951,8 @@ def main():
     roofline = wl.roofline(peak, peak_src)
     if world > 1 and args.workload == "combined" and not args.no_gather:
         recv = wl.units * NBINS * 4 * (world - 1)
-        roofline = {"bound": "hbm", "kernel": "NCCL all-gather of the spectrogram columns (link-bound step)",
+        roofline = {"bound": "hbm", "kernel": "all-gather of the spectrogram columns over NVLink (%s), link-bound step"
+                              % ("copy-engine pushes into peer memory" if args.transport == "peer" else "NCCL"),
                     "achieved": recv / (ms_per_step * 1e-3) / 1e9, "peak": 770.0, "unit": "GB/s",
                     "frac": recv / (ms_per_step * 1e-3) / 1e9 / 770.0, "traffic": None,
                     "peak_source": "measured NVLink peer copy, GB/s per direction per GPU (B200_PROFILING.md)",

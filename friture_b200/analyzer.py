@@ -119,13 +119,21 @@ class ChannelAnalyzer:
         return spec_host, bands_host
 
     # ------------------------------------------------------------------ multi-GPU path
-    def process_sharded(self, x, gathered, spec_chunks=None, bands=None, n_chunks=8, group=None):
+    def process_sharded(self, x, gathered=None, spec_chunks=None, bands=None, n_chunks=8, group=None,
+                        transport="peer"):
         """This rank's channels x [C, n_samples] plus the north-star's final all-gather of the
-        spectrogram columns.  The columns are produced in `n_chunks` frame chunks
-        (spec_chunks [n_chunks, C, F/n_chunks, nbins]); the all-gather of chunk i runs on a side
-        stream while chunk i+1 is transformed and while the filterbank kernel, which dominates the
-        step, runs on its own stream: the step costs max(compute, link), not their sum.
-        gathered: [n_chunks, world*C, F/n_chunks, nbins] (every rank ends with all columns).
+        spectrogram columns.  The columns are produced in `n_chunks` frame chunks; each chunk is on
+        its way to the other GPUs while the next one is transformed, and all of that hides behind
+        the filterbank kernel, which dominates the step: the step costs max(compute, link), not
+        their sum.  The (short, HBM-bound) transforms run first, the (long, latency-bound)
+        filterbank after them; the two compute kernels are NOT run side by side (see process()).
+
+        transport="peer"  copy-engine pushes into the peers' buffers over NVLink (friture_b200/peer.py):
+                          no SM takes part.  The gathered array [n_chunks, world, C, F/n_chunks, nbins]
+                          belongs to the analyzer (`self.peer_gather.gathered`); call
+                          `self.peer_gather.wait_all()` before reading other ranks' columns.
+        transport="nccl"  torch.distributed all_gather_into_tensor per chunk on a side stream into
+                          `gathered` [n_chunks, world*C, F/n_chunks, nbins].
         Returns (spec_chunks, bands, gathered)."""
         import torch
         import torch.distributed as dist
@@ -134,8 +142,6 @@ class ChannelAnalyzer:
         if F % n_chunks:
             raise ValueError("frames (%d) must divide into %d chunks" % (F, n_chunks))
         fc = F // n_chunks
-        if spec_chunks is None:
-            spec_chunks = torch.empty((n_chunks, C, fc, self.nbins), dtype=torch.float32, device=x.device)
         if bands is None:
             bands = torch.empty((C, B, self.nbands), dtype=torch.float32, device=x.device)
         cur = torch.cuda.current_stream(x.device)
@@ -143,22 +149,42 @@ class ChannelAnalyzer:
         for s in (s_stft, s_bank, s_comm):
             s.wait_stream(cur)
         self.proc._ensure_plan()
-        # the (short, HBM-bound) transforms first, chunk by chunk, each chunk's gather queued behind
-        # it on the communication stream; then the (long, latency-bound) filterbank, which the
-        # gathers overlap.  The two compute kernels are NOT run side by side (see process()).
+        pg = None
+        if transport == "peer":
+            key = (n_chunks, C, fc)
+            if getattr(self, "_pg_key", None) != key:
+                if getattr(self, "peer_gather", None) is not None:
+                    self.peer_gather.close()
+                from .peer import PeerGather
+                self.peer_gather = PeerGather(self.handle, n_chunks, (C, fc, self.nbins), group=group)
+                self._pg_key = key
+            pg = self.peer_gather
+            gathered = pg.gathered
+        elif transport == "nccl":
+            if spec_chunks is None:
+                spec_chunks = torch.empty((n_chunks, C, fc, self.nbins), dtype=torch.float32, device=x.device)
+        else:
+            raise ValueError("transport must be 'peer' or 'nccl'")
         for i in range(n_chunks):
+            dst = pg.local(i) if pg is not None else spec_chunks[i]
             with torch.cuda.stream(s_stft):
                 xi = x[:, i * fc * self.hop: (i * fc + fc - 1) * self.hop + self.fft_size]
                 self.handle.call("frt_stft_process", _lib._ptr(xi), int(x.stride(0)), int(C), int(fc),
-                                 int(self.hop), _lib._ptr(spec_chunks[i]), int(fc * self.nbins),
+                                 int(self.hop), _lib._ptr(dst), int(fc * self.nbins),
                                  int(self.nbins), _lib.STFT_LOGPOWER, _lib.current_stream_ptr(x.device))
-            s_comm.wait_stream(s_stft)
-            with torch.cuda.stream(s_comm):
-                dist.all_gather_into_tensor(gathered[i], spec_chunks[i], group=group)
+            if pg is not None:
+                pg.push(i, s_stft)
+            else:
+                s_comm.wait_stream(s_stft)
+                with torch.cuda.stream(s_comm):
+                    dist.all_gather_into_tensor(gathered[i], spec_chunks[i], group=group)
         s_bank.wait_stream(s_stft)
         with torch.cuda.stream(s_bank):
             self._bank(x, bands)
         cur.wait_stream(s_bank)
         cur.wait_stream(s_stft)
         cur.wait_stream(s_comm)
+        if pg is not None:
+            pg.join(cur)
+            spec_chunks = gathered[:, pg.rank]
         return spec_chunks, bands, gathered

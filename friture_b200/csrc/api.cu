@@ -147,3 +147,62 @@ extern "C" int frt_host_free(frt_handle h, void *p) {
     FRT_CUDA(h, cudaFreeHost(p));
     return FRT_OK;
 }
+
+// ---------------------------------------------------------------- NVLink peer memory
+// Buffers that other processes of the box can open (CUDA IPC) and write with the copy engines:
+// the transport of the final all-gather of spectrogram columns (friture_b200/peer.py).  A plain
+// cudaMalloc allocation is exportable as a whole; cudaMemcpyAsync between two devices' unified
+// addresses goes over NVLink/NVSwitch without occupying an SM.
+extern "C" int frt_peer_alloc(frt_handle h, size_t bytes, void **out) {
+    if (!h || !out) return frt_fail(h, FRT_EINVAL, "frt_peer_alloc: NULL argument");
+    DeviceGuard g(h->device);
+    *out = nullptr;
+    cudaError_t e = cudaMalloc(out, bytes ? bytes : 1);
+    if (e != cudaSuccess) return frt_fail(h, FRT_ENOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+    return FRT_OK;
+}
+
+extern "C" int frt_peer_free(frt_handle h, void *p) {
+    if (!p) return FRT_OK;
+    if (!h) return FRT_EINVAL;
+    DeviceGuard g(h->device);
+    FRT_CUDA(h, cudaFree(p));
+    return FRT_OK;
+}
+
+extern "C" int frt_peer_export(frt_handle h, void *p, void *handle64) {
+    if (!h || !p || !handle64) return frt_fail(h, FRT_EINVAL, "frt_peer_export: NULL argument");
+    DeviceGuard g(h->device);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+    cudaIpcMemHandle_t hd;
+    FRT_CUDA(h, cudaIpcGetMemHandle(&hd, p));
+    memcpy(handle64, &hd, sizeof(hd));
+    return FRT_OK;
+}
+
+extern "C" int frt_peer_import(frt_handle h, const void *handle64, void **out) {
+    if (!h || !handle64 || !out) return frt_fail(h, FRT_EINVAL, "frt_peer_import: NULL argument");
+    DeviceGuard g(h->device);
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handle64, sizeof(hd));
+    *out = nullptr;
+    FRT_CUDA(h, cudaIpcOpenMemHandle(out, hd, cudaIpcMemLazyEnablePeerAccess));
+    return FRT_OK;
+}
+
+extern "C" int frt_peer_close(frt_handle h, void *peer_ptr) {
+    if (!peer_ptr) return FRT_OK;
+    if (!h) return FRT_EINVAL;
+    DeviceGuard g(h->device);
+    FRT_CUDA(h, cudaIpcCloseMemHandle(peer_ptr));
+    return FRT_OK;
+}
+
+extern "C" int frt_peer_copy(frt_handle h, void *dst, const void *src, size_t bytes, void *stream) {
+    if (!h) return FRT_EINVAL;
+    if (!bytes) return FRT_OK;
+    if (!dst || !src) return frt_fail(h, FRT_EINVAL, "frt_peer_copy: NULL buffer");
+    DeviceGuard g(h->device);
+    FRT_CUDA(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    return FRT_OK;
+}

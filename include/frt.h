@@ -157,6 +157,19 @@ int frt_combined_process_host(frt_handle h, const float *x_host, int64_t x_strid
                               int64_t n_samples, int hop, float *spec_host, float *bands_host,
                               int nbands, int db);
 
+/* ---------------------------------------------------------------- NVLink peer memory
+ * Transport of the north-star's final all-gather of spectrogram columns: every process of the box
+ * allocates its gathered buffer here (a whole cudaMalloc allocation, exportable over CUDA IPC),
+ * exchanges the 64-byte handles, opens its peers' buffers and pushes its own columns into them with
+ * the copy engines (cudaMemcpyAsync over NVLink/NVSwitch): no SM takes part, so the transfers do
+ * not compete with the filterbank kernel for issue slots (friture_b200/peer.py).                   */
+int frt_peer_alloc(frt_handle h, size_t bytes, void **out);
+int frt_peer_free(frt_handle h, void *p);
+int frt_peer_export(frt_handle h, void *p, void *handle64);            /* cudaIpcGetMemHandle  */
+int frt_peer_import(frt_handle h, const void *handle64, void **out);   /* cudaIpcOpenMemHandle */
+int frt_peer_close(frt_handle h, void *peer_ptr);
+int frt_peer_copy(frt_handle h, void *dst, const void *src, size_t bytes, void *stream);
+
 /* ---------------------------------------------------------------- GCC-PHAT (delay estimator)
  * Stands behind `generalized_cross_correlation(d0, d1)` (friture/signal/correlation.py:24-43)
  * and the smoothing + peak pick around it (friture/delay_estimator.py:129-142).               */

@@ -83,25 +83,33 @@ from friture_b200.analyzer import ChannelAnalyzer
 from oracle import friture_oracle as fo
 C, F = 6, 16
 xs = [(np.random.default_rng(100 + r).standard_normal((C, (F + 1) * 1024)) * 0.1).astype(np.float32) for r in range(world)]
-an = ChannelAnalyzer(C)
-gathered = torch.empty((4, world * C, F // 4, 1025), dtype=torch.float32, device="cuda")
-chunks, bands, gathered = an.process_sharded(torch.from_numpy(xs[rank]).cuda(), gathered, n_chunks=4)
-torch.cuda.synchronize()
-# every rank must hold every rank's columns, in global channel order, equal to the oracle's
-full = gathered.permute(1, 0, 2, 3).reshape(world * C, F, 1025).cpu().numpy()
 ref = np.concatenate([fo.log_spectrogram(fo.stft_power_batch(x, 2048, 1024)) for x in xs], axis=0)
-err = float(np.max(np.abs(full - ref)) / max(np.max(np.abs(ref)), 1.0))
-own = chunks.permute(1, 0, 2, 3).reshape(C, F, 1025)
-same = bool(torch.equal(own, gathered.permute(1, 0, 2, 3).reshape(world * C, F, 1025)[rank * C:(rank + 1) * C]))
-print("RESULT rank %%d err %%.3g own_block_identical %%s" %% (rank, err, same), flush=True)
-assert err < 1e-5 and same
+for transport in ("nccl", "peer"):
+    an = ChannelAnalyzer(C)
+    gathered = torch.empty((4, world * C, F // 4, 1025), dtype=torch.float32, device="cuda") if transport == "nccl" else None
+    chunks, bands, gathered = an.process_sharded(torch.from_numpy(xs[rank]).cuda(), gathered, n_chunks=4,
+                                                 transport=transport)
+    if transport == "peer":
+        an.peer_gather.wait_all()           # every rank's pushes have landed
+    torch.cuda.synchronize()
+    # every rank must hold every rank's columns, in global channel order, equal to the oracle's
+    g = gathered.reshape(4, world * C, F // 4, 1025)
+    full = g.permute(1, 0, 2, 3).reshape(world * C, F, 1025).cpu().numpy()
+    err = float(np.max(np.abs(full - ref)) / max(np.max(np.abs(ref)), 1.0))
+    own = chunks.permute(1, 0, 2, 3).reshape(C, F, 1025)
+    same = bool(torch.equal(own, g.permute(1, 0, 2, 3).reshape(world * C, F, 1025)[rank * C:(rank + 1) * C]))
+    print("RESULT %%s rank %%d err %%.3g own_block_identical %%s" %% (transport, rank, err, same), flush=True)
+    assert err < 1e-5 and same
+    if transport == "peer":
+        an.peer_gather.close()
 dist.destroy_process_group()
 '''
 
 
-def test_nccl_gather_of_columns_two_ranks(tmp_path):
-    """north_star's collective on real NCCL: two ranks, the all-gather issued per frame chunk on a
-    side stream; gathered == the oracle's columns of all channels on every rank."""
+def test_gather_of_columns_two_ranks(tmp_path):
+    """north_star's collective on two real GPUs, both transports: NCCL all-gather per frame chunk on
+    a side stream, and copy-engine pushes into the peers' IPC-opened buffers over NVLink;
+    gathered == the oracle's columns of all channels on every rank."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
@@ -115,4 +123,4 @@ def test_nccl_gather_of_columns_two_ranks(tmp_path):
                           "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
                          capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
-    assert out.stdout.count("RESULT rank") == 2
+    assert out.stdout.count("RESULT nccl rank") == 2 and out.stdout.count("RESULT peer rank") == 2
