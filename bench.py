@@ -436,11 +436,11 @@ class Combined:
         self.bands = torch.empty((C, F + 1, 3 * n_oct), dtype=torch.float32, device=dev)
         self.gather = gather and world > 1
         self.n_chunks = 8 if F % 8 == 0 else 1
-        self.transport = transport
+        self.transport, self.engine = (transport.split("-") + ["auto"])[:2]
         if self.gather:
             fc = F // self.n_chunks
             self.spec_chunks = self.gathered = None
-            if transport == "nccl":
+            if self.transport == "nccl":
                 self.spec_chunks = torch.empty((self.n_chunks, C, fc, NBINS), dtype=torch.float32, device=dev)
                 self.gathered = torch.empty((self.n_chunks, world * C, fc, NBINS), dtype=torch.float32, device=dev)
             self.spec = None
@@ -455,7 +455,8 @@ class Combined:
         import torch
         if self.gather:
             self.spec_chunks, _, self.gathered = self.an.process_sharded(
-                self.x, self.gathered, self.spec_chunks, self.bands, self.n_chunks, transport=self.transport)
+                self.x, self.gathered, self.spec_chunks, self.bands, self.n_chunks, transport=self.transport,
+                engine=self.engine)
             return
         if timed:     # the dominant kernel's own duration, on the stream it runs on
             e0, e1 = event_pair()
@@ -825,9 +826,11 @@ def other_workloads(args, dev, rank, world, barrier, peak, peak_src):
         # reduction (one smoothed column per channel and tick instead of one per frame)
         res["combined_no_gather"] = quick(Combined, args.channels, args.frames, dev, rank, world, barrier, peak,
                                           peak_src, reps=5, gather=False)
-        other = "nccl" if args.transport == "peer" else "peer"
-        res["combined_gather_via_%s" % other] = quick(Combined, args.channels, args.frames, dev, rank, world, barrier,
-                                                      peak, peak_src, reps=5, transport=other)
+        auto = "peer-ce" if world <= 2 else "peer-kernel"
+        for other in ("nccl", "peer-ce", "peer-kernel"):
+            if other != args.transport and not (args.transport == "peer" and other == auto):
+                res["combined_gather_via_%s" % other] = quick(Combined, args.channels, args.frames, dev, rank, world,
+                                                              barrier, peak, peak_src, reps=5, transport=other)
         from friture_b200.spectrum import SpectrumAnalyzer
         from friture_b200.sharded import allgather_channels
         C, F = args.channels, args.frames
@@ -891,8 +894,9 @@ def main():
     ap.add_argument("--frames", type=int, default=None, help="hops / frames / blocks per channel per step")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-gather", action="store_true", help="N > 1: leave the all-gather out of the step")
-    ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
-                    help="N > 1: copy-engine pushes over NVLink peer memory (default) or NCCL all-gather")
+    ap.add_argument("--transport", default="peer", choices=["peer", "peer-ce", "peer-kernel", "nccl"],
+                    help="N > 1: one-hop pushes over NVLink peer memory (default; copy engines at 2 GPUs, a copy "
+                         "kernel from 4 up) or NCCL all-gather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-others", action="store_true")
@@ -963,7 +967,7 @@ def main():
     if world > 1 and args.workload == "combined" and not args.no_gather:
         recv = wl.units * NBINS * 4 * (world - 1)
         roofline = {"bound": "hbm", "kernel": "all-gather of the spectrogram columns over NVLink (%s), link-bound step"
-                              % ("copy-engine pushes into peer memory" if args.transport == "peer" else "NCCL"),
+                              % ("one-hop pushes into peer memory" if args.transport.startswith("peer") else "NCCL"),
                     "achieved": recv / (ms_per_step * 1e-3) / 1e9, "peak": 770.0, "unit": "GB/s",
                     "frac": recv / (ms_per_step * 1e-3) / 1e9 / 770.0, "traffic": None,
                     "peak_source": "measured NVLink peer copy, GB/s per direction per GPU (B200_PROFILING.md)",

@@ -54,6 +54,7 @@ SIGNATURES = {
     "frt_peer_import": (c_int, [c_void_p, c_void_p, POINTER(c_void_p)]),
     "frt_peer_close": (c_int, [c_void_p, c_void_p]),
     "frt_peer_copy": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "frt_peer_push": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_size_t, c_int, c_void_p]),
     "frt_stft_plan": (c_int, [c_void_p, c_int]),
     "frt_stft_window": (c_int, [c_void_p, c_void_p]),
     "frt_stft_process": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int64, c_int, c_void_p,

@@ -120,7 +120,7 @@ class ChannelAnalyzer:
 
     # ------------------------------------------------------------------ multi-GPU path
     def process_sharded(self, x, gathered=None, spec_chunks=None, bands=None, n_chunks=8, group=None,
-                        transport="peer"):
+                        transport="peer", engine="auto"):
         """This rank's channels x [C, n_samples] plus the north-star's final all-gather of the
         spectrogram columns.  The columns are produced in `n_chunks` frame chunks; each chunk is on
         its way to the other GPUs while the next one is transformed, and all of that hides behind
@@ -128,8 +128,8 @@ class ChannelAnalyzer:
         their sum.  The (short, HBM-bound) transforms run first, the (long, latency-bound)
         filterbank after them; the two compute kernels are NOT run side by side (see process()).
 
-        transport="peer"  copy-engine pushes into the peers' buffers over NVLink (friture_b200/peer.py):
-                          no SM takes part.  The gathered array [n_chunks, world, C, F/n_chunks, nbins]
+        transport="peer"  one-hop pushes into the peers' IPC-opened buffers over NVLink (friture_b200/peer.py):
+                          copy engines at 2 GPUs, a small copy kernel from 4 GPUs up (engine="ce"|"kernel").  The gathered array [n_chunks, world, C, F/n_chunks, nbins]
                           belongs to the analyzer (`self.peer_gather.gathered`); call
                           `self.peer_gather.wait_all()` before reading other ranks' columns.
         transport="nccl"  torch.distributed all_gather_into_tensor per chunk on a side stream into
@@ -151,12 +151,12 @@ class ChannelAnalyzer:
         self.proc._ensure_plan()
         pg = None
         if transport == "peer":
-            key = (n_chunks, C, fc)
+            key = (n_chunks, C, fc, engine)
             if getattr(self, "_pg_key", None) != key:
                 if getattr(self, "peer_gather", None) is not None:
                     self.peer_gather.close()
                 from .peer import PeerGather
-                self.peer_gather = PeerGather(self.handle, n_chunks, (C, fc, self.nbins), group=group)
+                self.peer_gather = PeerGather(self.handle, n_chunks, (C, fc, self.nbins), group=group, engine=engine)
                 self._pg_key = key
             pg = self.peer_gather
             gathered = pg.gathered

@@ -206,3 +206,54 @@ extern "C" int frt_peer_copy(frt_handle h, void *dst, const void *src, size_t by
     FRT_CUDA(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
     return FRT_OK;
 }
+
+// One-hop all-gather push over NVLink: every CTA streams slices of this rank's block from local
+// HBM (read ONCE) into the same offset of up to 15 peers' buffers with 128-bit stores.  A handful
+// of CTAs keeps enough stores in flight to fill the links; each of their warps issues one load and
+// n_peers stores per 512 bytes, so the kernel takes almost no issue slots from the filterbank
+// kernel it overlaps (NCCL's all-gather moves the same bytes through ring steps with copy kernels
+// that occupy whole SMs; the copy engines alone top out near 430 GB/s per GPU, measured).
+struct PeerPushArgs {
+    const float4 *src;
+    float4 *dst[15];
+    int n_peers;
+    long long n_vec;      // float4 elements
+};
+
+__global__ void __launch_bounds__(256) peer_push_kernel(const PeerPushArgs a) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n_vec; i += 4 * stride) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (i + u * stride < a.n_vec) v[u] = __ldcs(a.src + i + u * stride);
+        for (int p = 0; p < a.n_peers; p++) {
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (i + u * stride < a.n_vec) a.dst[p][i + u * stride] = v[u];
+        }
+    }
+}
+
+extern "C" int frt_peer_push(frt_handle h, const void *src, void *const *peer_dst, int n_peers,
+                             size_t bytes, int n_ctas, void *stream) {
+    if (!h) return FRT_EINVAL;
+    if (!bytes || n_peers == 0) return FRT_OK;
+    DeviceGuard g(h->device);
+    FRT_CHECK_ARG(h, src && peer_dst, "NULL buffer");
+    FRT_CHECK_ARG(h, n_peers >= 1 && n_peers <= 15, "n_peers must be in [1, 15]");
+    FRT_CHECK_ARG(h, bytes % 16 == 0 && ((uintptr_t)src & 15) == 0, "16-byte aligned blocks only");
+    PeerPushArgs a;
+    a.src = reinterpret_cast<const float4 *>(src);
+    for (int p = 0; p < n_peers; p++) {
+        FRT_CHECK_ARG(h, peer_dst[p] && ((uintptr_t)peer_dst[p] & 15) == 0, "peer pointer NULL or unaligned");
+        a.dst[p] = reinterpret_cast<float4 *>(peer_dst[p]);
+    }
+    a.n_peers = n_peers;
+    a.n_vec = (long long)(bytes / 16);
+    if (n_ctas < 1) n_ctas = 32;
+    peer_push_kernel<<<n_ctas, 256, 0, (cudaStream_t)stream>>>(a);
+    h->launches++;
+    FRT_CUDA(h, cudaGetLastError());
+    return FRT_OK;
+}

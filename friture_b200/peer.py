@@ -1,4 +1,4 @@
-"""All-gather over NVLink peer memory, driven by the copy engines.
+"""All-gather over NVLink peer memory: one-hop pushes by the copy engines or by a small copy kernel.
 
 The north-star's one collective is the final all-gather of the spectrogram columns: every GPU must
 receive (N-1)/N of ALL columns, about 3.8 GB per GPU and step at 8 x 1024 channels -- link-bound by
@@ -8,8 +8,12 @@ step for 0.7 ms of link time).  Here every rank allocates its gathered buffer th
 (``frt_peer_alloc``: a whole ``cudaMalloc`` allocation, exportable over CUDA IPC), the ranks exchange
 the 64-byte handles, open each other's buffers, and every rank PUSHES its own block into its peers'
 buffers with ``cudaMemcpyAsync`` on one stream per peer: the copy engines drive NVLink/NVSwitch, no
-SM is involved, and the transfers overlap the compute for free.  The rank's own block is written
-in place by the STFT kernel (``local(i)`` is a view of the gathered buffer).
+SM is involved, and the transfers overlap the compute for free.  The copy engines of one GPU top out
+near 430 GB/s (measured at N = 8, where 7/8 of 4.3 GB must leave every GPU per step), so from 4 GPUs
+up the push is done by ``frt_peer_push`` instead: 32 CTAs that read the block once from local HBM and
+store it to all peers with 128-bit stores -- one hop, no ring steps, a few warps' worth of issue
+slots.  The rank's own block is written in place by the STFT kernel (``local(i)`` is a view of the
+gathered buffer).
 """
 from __future__ import annotations
 
@@ -36,7 +40,7 @@ class PeerGather:
     wait_all()          join + device sync + group barrier: every rank's data has landed here
     """
 
-    def __init__(self, handle, n_blocks, block_shape, group=None):
+    def __init__(self, handle, n_blocks, block_shape, group=None, engine="auto", n_ctas=32):
         import torch
         import torch.distributed as dist
         self.handle = handle
@@ -56,8 +60,14 @@ class PeerGather:
         self._ptr = p.value
         self.gathered = torch.as_tensor(_DevBuf(self._ptr, (self.n_blocks, self.world) + self.block_shape),
                                         device=self.device)
+        # "ce": one cudaMemcpyAsync per peer (copy engines, no SM at all; ~430 GB/s per GPU measured,
+        # the best choice at 2 GPUs); "kernel": frt_peer_push, a small copy kernel that reads the block
+        # once and stores it to every peer (fills the links from 4 GPUs up)
+        self.engine = ("ce" if self.world <= 2 else "kernel") if engine == "auto" else engine
+        self.n_ctas = int(n_ctas)
         self._peers = [None] * self.world
         self._streams = [None] * self.world
+        self._push_stream = None
         if self.world > 1:
             mine = ctypes.create_string_buffer(64)
             handle.call("frt_peer_export", c_void_p(self._ptr), mine)
@@ -70,6 +80,10 @@ class PeerGather:
                 handle.call("frt_peer_import", ctypes.create_string_buffer(handles[r], 64), ctypes.byref(q))
                 self._peers[r] = q.value
                 self._streams[r] = torch.cuda.Stream(self.device)
+            self._push_stream = torch.cuda.Stream(self.device, priority=-1)
+            order = [(self.rank + k) % self.world for k in range(1, self.world)]   # stagger the targets
+            self._order = order
+            self._peer_table = (c_void_p * len(order))()
             dist.barrier(group=group)
 
     def local(self, i):
@@ -79,6 +93,14 @@ class PeerGather:
         """Queue the copies of this rank's block i into every peer's buffer behind stream `after`."""
         off = (i * self.world + self.rank) * self.block_bytes
         src = c_void_p(self._ptr + off)
+        if self.world > 1 and self.engine == "kernel":
+            for n, r in enumerate(self._order):
+                self._peer_table[n] = self._peers[r] + off
+            st = self._push_stream
+            st.wait_stream(after)
+            self.handle.call("frt_peer_push", src, self._peer_table, len(self._order), c_size_t(self.block_bytes),
+                             self.n_ctas, c_void_p(st.cuda_stream))
+            return
         for k in range(1, self.world):
             r = (self.rank + k) % self.world         # stagger the targets over the ranks
             st = self._streams[r]
@@ -87,7 +109,7 @@ class PeerGather:
                              c_void_p(st.cuda_stream))
 
     def join(self, stream):
-        for st in self._streams:
+        for st in self._streams + [self._push_stream]:
             if st is not None:
                 stream.wait_stream(st)
 

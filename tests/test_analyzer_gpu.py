@@ -84,11 +84,11 @@ from oracle import friture_oracle as fo
 C, F = 6, 16
 xs = [(np.random.default_rng(100 + r).standard_normal((C, (F + 1) * 1024)) * 0.1).astype(np.float32) for r in range(world)]
 ref = np.concatenate([fo.log_spectrogram(fo.stft_power_batch(x, 2048, 1024)) for x in xs], axis=0)
-for transport in ("nccl", "peer"):
+for transport, engine in (("nccl", "auto"), ("peer", "ce"), ("peer", "kernel")):
     an = ChannelAnalyzer(C)
     gathered = torch.empty((4, world * C, F // 4, 1025), dtype=torch.float32, device="cuda") if transport == "nccl" else None
     chunks, bands, gathered = an.process_sharded(torch.from_numpy(xs[rank]).cuda(), gathered, n_chunks=4,
-                                                 transport=transport)
+                                                 transport=transport, engine=engine)
     if transport == "peer":
         an.peer_gather.wait_all()           # every rank's pushes have landed
     torch.cuda.synchronize()
@@ -98,7 +98,7 @@ for transport in ("nccl", "peer"):
     err = float(np.max(np.abs(full - ref)) / max(np.max(np.abs(ref)), 1.0))
     own = chunks.permute(1, 0, 2, 3).reshape(C, F, 1025)
     same = bool(torch.equal(own, g.permute(1, 0, 2, 3).reshape(world * C, F, 1025)[rank * C:(rank + 1) * C]))
-    print("RESULT %%s rank %%d err %%.3g own_block_identical %%s" %% (transport, rank, err, same), flush=True)
+    print("RESULT %%s-%%s rank %%d err %%.3g own_block_identical %%s" %% (transport, engine, rank, err, same), flush=True)
     assert err < 1e-5 and same
     if transport == "peer":
         an.peer_gather.close()
@@ -123,4 +123,5 @@ def test_gather_of_columns_two_ranks(tmp_path):
                           "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
                          capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
-    assert out.stdout.count("RESULT nccl rank") == 2 and out.stdout.count("RESULT peer rank") == 2
+    assert out.stdout.count("RESULT nccl-auto rank") == 2
+    assert out.stdout.count("RESULT peer-ce rank") == 2 and out.stdout.count("RESULT peer-kernel rank") == 2
