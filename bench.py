@@ -447,8 +447,11 @@ class Combined:
         else:
             self.spec = torch.empty((C, F, NBINS), dtype=torch.float32, device=dev)
         self.units = C * F
-        # our kernels per step (the copy-engine pushes / NCCL kernels are not ours)
+        # our kernels per step (copy-engine pushes / NCCL kernels are not ours, the push kernel is)
         self.launches_per_step = (1 + self.n_chunks) if self.gather else 2
+        if self.gather and self.transport == "peer" and (self.engine == "kernel" or
+                                                         (self.engine == "auto" and world > 2)):
+            self.launches_per_step += self.n_chunks
         self.bank_events = []
 
     def step(self, timed=False):
