@@ -655,15 +655,20 @@ extern "C" int frt_bank_set_weighting(frt_handle h, const float *weight_db_host)
     return FRT_OK;
 }
 
-extern "C" int frt_bank_schedule(int n_octaves, int log2_chunk, int64_t n_samples, int *stage_start,
-                                 int *n_steps) {
+extern "C" int frt_bank_schedule2(int n_octaves, int log2_chunk, int sections_per_lane, int64_t n_samples,
+                                  int *stage_start, int *n_steps) {
     if (n_octaves < 1 || n_octaves > MAX_OCT || (log2_chunk != 5 && log2_chunk != 6) || !stage_start ||
-        n_samples < 0)
+        n_samples < 0 || (sections_per_lane != 1 && sections_per_lane != 2))
         return FRT_EINVAL;
     int T[BANK_MAX_OCT + 1];
-    frt_pipe_schedule(n_octaves, log2_chunk, n_samples, T, n_steps);
+    frt_pipe_schedule(n_octaves, log2_chunk, sections_per_lane, n_samples, T, n_steps);
     for (int j = 0; j < MAX_OCT; j++) stage_start[j] = T[j];
     return FRT_OK;
+}
+
+extern "C" int frt_bank_schedule(int n_octaves, int log2_chunk, int64_t n_samples, int *stage_start,
+                                 int *n_steps) {
+    return frt_bank_schedule2(n_octaves, log2_chunk, 2, n_samples, stage_start, n_steps);
 }
 
 extern "C" int frt_bank_state_size(frt_handle h, int64_t *z_floats, int64_t *ema_floats) {
@@ -832,10 +837,17 @@ static int bank_process_impl(frt_handle h, const float *x_dev, int64_t x_stride,
         // gives the same bits however it is cut into launches.
         int pack = pl->n_channels > 3072 ? 2 : 1;
         int logch = (block >= 512 && pl->n_channels <= 3072) ? 6 : 5;
+        int spl = 2;
+        const char *force_s = getenv("FRT_BANK_SPL");
         if (force_p) pack = force_p[0] == '2' ? 2 : 1;
         if (force_c) logch = force_c[0] == '6' ? 6 : 5;
-        while (logch > 5 && block < (4 << logch)) logch--;
-        e = frt_pipe_launch(pl, a, logch, pack, st);
+        if (force_s) spl = force_s[0] == '1' ? 1 : 2;
+        // fall back to shorter steps, then to the half-warp layout, when the block is too short for the
+        // variant's pipeline depth (frt_pipe_supported)
+        while (logch > 5 && !frt_pipe_supported(pl, block, logch, spl)) logch--;
+        if (!frt_pipe_supported(pl, block, logch, spl)) spl = 2;
+        while (logch > 5 && !frt_pipe_supported(pl, block, logch, spl)) logch--;
+        e = frt_pipe_launch(pl, a, logch, pack, spl, st);
     } else if (tile == 1024) e = launch_bank<32>(pl, a, st);
     else if (tile == 512) e = launch_bank<16>(pl, a, st);
     else e = launch_bank<8>(pl, a, st);

@@ -70,7 +70,7 @@ struct BankArgs {
 
 struct BankPlan {
     BankParams params;
-    PipeParams pipe[2];    // [0]: 32-sample steps, [1]: 64-sample steps
+    PipeParams pipe[4];    // [2*(logch-5) + (2-spl)]: 32 / 64-sample steps x two / one section per lane
     bool pipe_ok = false;  // the lane-pipelined kernel supports this bank
     int n_channels = 0;
     float *zstate = nullptr;
@@ -82,7 +82,8 @@ struct BankPlan {
 
 // bank_pipe.cu
 void frt_pipe_prepare(BankPlan *pl);
-void frt_pipe_schedule(int n_oct, int logch, long long t_total, int *T /*[BANK_MAX_OCT+1]*/,
+void frt_pipe_schedule(int n_oct, int logch, int spl, long long t_total, int *T /*[BANK_MAX_OCT+1]*/,
                        int *n_steps);
-int frt_pipe_flush_delta(int n_oct, int logch, const int *T);
-cudaError_t frt_pipe_launch(const BankPlan *pl, BankArgs a, int logch, int pack, cudaStream_t st);
+int frt_pipe_flush_delta(int n_oct, int logch, int spl, const int *T);
+bool frt_pipe_supported(const BankPlan *pl, int block, int logch, int spl);
+cudaError_t frt_pipe_launch(const BankPlan *pl, BankArgs a, int logch, int pack, int spl, cudaStream_t st);

@@ -44,7 +44,20 @@
 
 namespace {
 
-constexpr int DEC_DEPTH = 3;     // decimator chain = 3 lanes: a stage trails its parent by 3 steps
+// Two lane layouts, SPL = sections per lane:
+//   SPL = 2  one half-warp per channel (pair), roles as described above, decimator chain 3 lanes deep;
+//   SPL = 1  one WARP per channel (pair): NR = 2 bpo + 6 roles per group, role r = section r, a band is a
+//            chain of two lanes (its output trails the stage input by one step), the decimator a chain
+//            of six.  Half the serial work per lane and step: the kernel is bound by the latency of
+//            one warp's instruction stream up to ~1000 channels (its duration barely moves between 1
+//            and 1024 channels), so this is the layout for few channels.
+template <int SPL> struct Geo {
+    static constexpr int HW = SPL == 2 ? 16 : 32;      // lanes per channel slot
+    static constexpr int NSLOT = 32 / HW;               // channel slots per warp
+    static constexpr int DD = SPL == 2 ? 3 : 6;         // decimator chain depth in lanes = steps a stage trails its parent
+    static constexpr int BSK = SPL == 2 ? 0 : 1;        // steps the band outputs trail the stage input
+    static constexpr int RS = 2 * SPL;                  // state values per role
+};
 
 template <int PACK> struct VT;
 template <> struct VT<1> { using t = float; };
@@ -118,7 +131,10 @@ __device__ __forceinline__ float lg2_fast(float v) {
     return r;
 }
 
-constexpr int EN_RING = 8;      // blocks of band energies staged in shared memory before the flush
+// blocks of band energies staged in shared memory before the flush: a block's vector leaves fdelta
+// steps after its last stage-0 chunk, meanwhile stage 0 keeps staging newer blocks
+// (frt_pipe_supported checks that the ring is deep enough for the block length)
+template <int SPL> struct EnRing { static constexpr int N = SPL == 2 ? 8 : 16; };
 
 // The two lane groups of a half-warp must run ONE instruction stream with per-lane predicates.
 // Conditions on the (loop-invariant) group index invite the compiler to unswitch the whole
@@ -163,59 +179,64 @@ __host__ __device__ constexpr bool seg_starts_at(int slot, int ch) {
 #ifndef PIPE_MINB5
 #define PIPE_MINB5 16
 #endif
-__host__ __device__ constexpr int pipe_min_blocks(int logch, int pack) {
-    return (logch == 5 && pack == 1) ? PIPE_MINB5 : (logch == 6 && pack == 1) ? 12 : 8;
+__host__ __device__ constexpr int pipe_min_blocks(int logch, int pack, int spl) {
+    return spl == 1 ? 8 : (logch == 5 && pack == 1) ? PIPE_MINB5 : (logch == 6 && pack == 1) ? 12 : 8;
 }
 
-template <int LOGCH, int PACK, int BPO>
+template <int LOGCH, int PACK, int BPO, int SPL>
 struct PipeLayout {
     static constexpr int CH = 1 << LOGCH;
-    static constexpr int NR = BPO + DEC_DEPTH;
+    static constexpr int NR = (BPO + 3) * (2 / SPL);
+    static constexpr int RS = 2 * SPL;
+    static constexpr int NWR = SPL == 2 ? 12 : 2 * NR;        // writer lanes
+    static constexpr int WPAD = SPL == 2 ? 4 : (8 - NWR % 8) % 8;
     static constexpr int TB = 4 * PACK;                       // bytes per T
     static constexpr int PAD = 16 / TB;                       // 16 bytes
     static constexpr int XSLOT = 2 * CH + 8 * PAD;            // ring slot: 128 B of skew + 2 vectors
     static constexpr int X0 = 5 * PAD;                        // stage-0 chunk within a slot (group 5)
     static constexpr int XM = X0 + CH + PAD;                  // multiplexed vector (group 6)
     static constexpr int X = 0;                               // [RX][XSLOT]
-    static constexpr int W = X + PIPE_RX * XSLOT;             // [12 writer lanes][2 bufs][CH] + 16 B each
+    static constexpr int W = X + PIPE_RX * XSLOT;             // [NWR writer lanes][2 bufs][CH] + 16 B each
     static constexpr int WSTR = 2 * CH + PAD;
-    static constexpr int S = W + 12 * WSTR + 4 * PAD;         // [MAX_OCT][NR][4]: z1A z2A z1B z2B
-    static constexpr int ER = S + BANK_MAX_OCT * NR * 4;      // [MAX_OCT][4]: ruler-stage energies
+    static constexpr int S = W + NWR * WSTR + WPAD * PAD;     // [MAX_OCT][NR][RS]: z1A z2A (z1B z2B)
+    static constexpr int ER = S + BANK_MAX_OCT * NR * RS;     // [MAX_OCT][4]: ruler-stage energies
     static constexpr int MB = ER + BANK_MAX_OCT * 4;          // [MAX_OCT + 2][2] mailboxes
     static constexpr int EN = MB + (BANK_MAX_OCT + 2) * 2;    // [EN_RING][32] staged band energies
-    static constexpr int RAW = EN + EN_RING * 32;
+    static constexpr int RAW = EN + EnRing<SPL>::N * 32;
     // round up to 64 (mod 128) bytes
     static constexpr int RAWB = RAW * TB;
     static constexpr int TOTALB = ((RAWB + 63) / 128) * 128 + 64;
     static constexpr int TOTAL = TOTALB / TB;
-    static_assert((12 * WSTR + 4 * PAD) % (8 * PAD) == 0, "state rows start on a 128-byte boundary");
+    static_assert((NWR * WSTR + WPAD * PAD) % (8 * PAD) == 0, "state rows start on a 128-byte boundary");
 };
 
-template <int LOGCH, int PACK, int BPO>
-__global__ void __launch_bounds__(32, pipe_min_blocks(LOGCH, PACK))
+template <int LOGCH, int PACK, int BPO, int SPL>
+__global__ void __launch_bounds__(32, pipe_min_blocks(LOGCH, PACK, SPL))
 bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
     using T = typename VT<PACK>::t;
-    using LY = PipeLayout<LOGCH, PACK, BPO>;
-    constexpr int CH = 1 << LOGCH, JR = LOGCH + 1, NR = LY::NR, NSEC = 2 * NR;
-    constexpr int NSL = CH / 16;              // sample slots per lane of the half-warp (phase B)
+    using LY = PipeLayout<LOGCH, PACK, BPO, SPL>;
+    constexpr int HW = Geo<SPL>::HW, NSLOT = Geo<SPL>::NSLOT, DEC_DEPTH = Geo<SPL>::DD, BSK = Geo<SPL>::BSK,
+                  RS = Geo<SPL>::RS;
+    constexpr int CH = 1 << LOGCH, JR = LOGCH + 1, NR = LY::NR, NSEC = SPL * NR, EN_RING = EnRing<SPL>::N;
+    constexpr int NSL = CH / HW;              // sample slots per lane of the channel slot (phase B)
     constexpr int NG = CH / 4;                // 4-sample groups per step
     constexpr int GB = (PACK == 1 ? 32 : 16) / 4;   // groups whose inputs are loaded ahead
     constexpr int RX = PIPE_RX, PF = PIPE_PF;
-    static_assert(2 * NR <= 16, "two lane groups must fit in a half-warp");
+    static_assert(2 * NR <= HW, "two lane groups must fit in a channel slot");
     static_assert(LOGCH == 5 || LOGCH == 6, "steps of 32 or 64 samples");
     static_assert(NG % GB == 0, "whole load batches");
 
     extern __shared__ __align__(128) float4 smem4[];
     const int lane = threadIdx.x;
-    const int h = lane >> 4, hl = lane & 15;
-    T *sm = reinterpret_cast<T *>(smem4) + h * LY::TOTAL;       // this half-warp's channel slot
-    int *sT = reinterpret_cast<int *>(reinterpret_cast<T *>(smem4) + 2 * LY::TOTAL);   // [MAX_OCT + 2]
+    const int h = lane / HW, hl = lane & (HW - 1);
+    T *sm = reinterpret_cast<T *>(smem4) + h * LY::TOTAL;       // this channel slot
+    int *sT = reinterpret_cast<int *>(reinterpret_cast<T *>(smem4) + NSLOT * LY::TOTAL);   // [MAX_OCT + 2]
     float *sAl = reinterpret_cast<float *>(sT + 12);            // [MAX_OCT + 2]
     T *sX = sm + LY::X, *sW = sm + LY::W, *sS = sm + LY::S, *sER = sm + LY::ER, *sMB = sm + LY::MB,
       *sEN = sm + LY::EN;
 
     // channels of this half-warp (clamped when the last warp is not full; `alive` gates the writes)
-    const int cgrp = blockIdx.x * 2 + h;
+    const int cgrp = blockIdx.x * NSLOT + h;
     const bool alive = cgrp * PACK < a.n_channels;
     const int ch0 = alive ? cgrp * PACK : 0;
     const bool has2 = (PACK == 2) && alive && (ch0 + 1 < a.n_channels);
@@ -234,14 +255,17 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
     const bool worker = hl < 2 * NR;
     const int G = (worker && hl >= NR) ? 1 : 0;
     const int r = worker ? hl - G * NR : 0;
-    const bool isband = r < BPO;
-    const int d = isband ? 0 : r - BPO;                      // skew = position in the decimator chain
+    const bool isband = r < BPO * (2 / SPL);
+    const int band = SPL == 2 ? r : (r >> 1);
+    const bool isout = isband && (SPL == 2 || (r & 1));      // this lane's output is the band signal
+    // skew = position in the lane chain (band: 2 lanes when SPL = 1; decimator: DEC_DEPTH lanes)
+    const int d = isband ? (SPL == 2 ? 0 : (r & 1)) : r - BPO * (2 / SPL);
     const bool isdec2 = worker && (r == NR - 1);
     const bool ishead = (d == 0);                            // reads the stage input
     const int maxstage = isband ? n_oct - 1 : n_oct - 2;     // the last stage's decimator is unused (filter.py:113)
-    const float cA = P.c[2 * r], n1A = P.na1[2 * r], n2A = P.na2[2 * r];
-    const float cB = P.c[2 * r + 1], n1B = P.na1[2 * r + 1], n2B = P.na2[2 * r + 1];
-    const float gb_lane = isband ? P.gband[r] : 0.f;
+    const float cA = P.c[SPL * r], n1A = P.na1[SPL * r], n2A = P.na2[SPL * r];
+    const float cB = P.c[SPL * r + SPL - 1], n1B = P.na1[SPL * r + SPL - 1], n2B = P.na2[SPL * r + SPL - 1];
+    const float gb_lane = isband ? P.gband[band] : 0.f;
     const float gdec = P.gdec;
 
     // ---- prologue: tables, state
@@ -253,27 +277,27 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
     float *gz1 = a.zstate + (size_t)ch1 * n_oct * NSEC * 2;
     float *ge0 = a.ema + (size_t)ch0 * nbands;
     float *ge1 = a.ema + (size_t)ch1 * nbands;
-    for (int i = hl; i < BANK_MAX_OCT * NSEC * 2; i += 16) {    // sS[j][r][4] == global z[j][2r .. 2r+1][2]
+    for (int i = hl; i < BANK_MAX_OCT * NSEC * 2; i += HW) {    // sS[j][r][RS] == global z[j][SPL r ..][2]
         T z;
         v_set(z, 0.f, 0.f);
         if (i < n_oct * NSEC * 2) v_set(z, gz0[i], gz1[i]);
         sS[i] = z;
     }
-    for (int i = hl; i < BANK_MAX_OCT * 4; i += 16) {
+    for (int i = hl; i < BANK_MAX_OCT * 4; i += HW) {
         const int j = i >> 2, b = i & 3;
         T e;
         v_set(e, 0.f, 0.f);
         if (j >= JR && j < n_oct && b < BPO) v_set(e, ge0[j * BPO + b], ge1[j * BPO + b]);
         sER[i] = e;
     }
-    // smoothing accumulators: one per sample slot (slot = hl + 16 q) of the two band-output vectors
+    // smoothing accumulators: one per sample slot (slot = hl + HW q) of the two band-output vectors
     T acc0[BPO][NSL], accm[BPO][NSL];
     int mst[NSL];
     bool mok[NSL], lastslot[NSL];
     float om0[NSL], aqm[NSL], omm[NSL];
 #pragma unroll
     for (int q = 0; q < NSL; q++) {
-        const int p = hl + 16 * q;
+        const int p = hl + HW * q;
         const int j = 1 + __clz(~((unsigned)p << (32 - LOGCH)));     // stage owning slot p
         mst[q] = j;
         mok[q] = (j < JR) && (j <= n_oct - 1);
@@ -300,7 +324,7 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
             } else {
 #pragma unroll
                 for (int q = 0; q < NSL; q++) {
-                    const int p = hl + 16 * q;
+                    const int p = hl + HW * q;
                     float *dd = reinterpret_cast<float *>(dst + p);
                     cp_async4(dd, x0 + (size_t)cn * CH + p);
                     if (PACK == 2) cp_async4(dd + 1, x1 + (size_t)cn * CH + p);
@@ -315,9 +339,9 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
     __syncwarp();
 
     // stage-0 lanes carry their section state in registers from step to step
-    T zc[4];
+    T zc[RS];
 #pragma unroll
-    for (int i = 0; i < 4; i++) zc[i] = sS[r * 4 + i];
+    for (int i = 0; i < RS; i++) zc[i] = sS[r * RS + i];
     const int n_steps = a.n_steps;
     // steps in [k_lo, k_hi) have every slot of every lane valid (pipeline full, nothing drained):
     // they run the variant without the range checks
@@ -347,12 +371,12 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
         // rows of sS at every segment start, the next row is fetched one segment ahead.  Loads are
         // unconditional (group 0 reads rows it never uses), selection is by per-lane predicate.
         const bool g1 = opq(G != 0);
-        T cur[4], nxt[4];
-        T *spc = sS + (1 * NR + r) * 4;        // state row of the segment being processed (group 1)
+        T cur[RS], nxt[RS];
+        T *spc = sS + (1 * NR + r) * RS;       // state row of the segment being processed (group 1)
 #pragma unroll
-        for (int i = 0; i < 4; i++) cur[i] = v_sel(g1, spc[i], zc[i]);
+        for (int i = 0; i < RS; i++) cur[i] = v_sel(g1, spc[i], zc[i]);
 #pragma unroll
-        for (int i = 0; i < 4; i++) nxt[i] = sS[(2 * NR + r) * 4 + i];
+        for (int i = 0; i < RS; i++) nxt[i] = sS[(2 * NR + r) * RS + i];
         bool pvc = !CHECK || ((unsigned)(u - DEC_DEPTH) < (unsigned)n_chunks && 1 <= maxstage);
         bool pvB = false;           // validity / chunk index of the 1-sample stage LOGCH (for the mailbox)
         int cidxB = 0;
@@ -378,16 +402,16 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
                         const bool gs = opq(G != 0);
                         if (gs && pvc) {
 #pragma unroll
-                            for (int e = 0; e < 4; e++) spc[e] = cur[e];
+                            for (int e = 0; e < RS; e++) spc[e] = cur[e];
                         }
 #pragma unroll
-                        for (int e = 0; e < 4; e++) cur[e] = v_sel(gs, nxt[e], cur[e]);
-                        spc = (g < LOGCH) ? sS + ((g + 1) * NR + r) * 4 : sS + (jrc * NR + r) * 4;
+                        for (int e = 0; e < RS; e++) cur[e] = v_sel(gs, nxt[e], cur[e]);
+                        spc = (g < LOGCH) ? sS + ((g + 1) * NR + r) * RS : sS + (jrc * NR + r) * RS;
                         if (g < LOGCH) {
-                            const T *spn = (g + 1 < LOGCH) ? sS + ((g + 2) * NR + r) * 4
-                                                           : sS + (jrc * NR + r) * 4;
+                            const T *spn = (g + 1 < LOGCH) ? sS + ((g + 2) * NR + r) * RS
+                                                           : sS + (jrc * NR + r) * RS;
 #pragma unroll
-                            for (int e = 0; e < 4; e++) nxt[e] = spn[e];
+                            for (int e = 0; e < RS; e++) nxt[e] = spn[e];
                             pvc = !CHECK || ((unsigned)(u - DEC_DEPTH * (g + 1)) < (unsigned)n_chunks &&
                                              (g + 1) <= maxstage);
                             if (g == LOGCH - 1) {
@@ -399,7 +423,8 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
                         }
                     }
                     const T ya = biquad(v[q][i], cur[0], cur[1], cA, n1A, n2A);
-                    y[i] = biquad(ya, cur[2], cur[3], cB, n1B, n2B);
+                    if (SPL == 2) y[i] = biquad(ya, cur[RS - 2], cur[RS - 1], cB, n1B, n2B);
+                    else y[i] = ya;
                 }
                 const int gq = b0 + q;
                 if (gq < NG - 1) {
@@ -416,16 +441,16 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
                         if (gl && pvB && !(cidxB & 1)) sMB[JR * 2 + ((cidxB >> 1) & 1)] = v_mul(gdec, y[2]);
                         if (gl && pvR && !(m & 1)) sMB[(jrc + 1) * 2 + ((m >> 1) & 1)] = v_mul(gdec, y[3]);
                     }
-                    if (gl && isband) {
+                    if (gl && isout) {
                         // exp_smoothed_value of the low-rate stages: e <- (1-alpha) e + y^2 (e/alpha form)
                         const float alj = sAl[jrc];
-                        T e = sER[jrc * 4 + r];
+                        T e = sER[jrc * 4 + band];
                         e = v_add(v_fma(-alj, e, e), v_sq(y[3]));      // raw units
                         if (pvR) {
-                            sER[jrc * 4 + r] = e;
+                            sER[jrc * 4 + band] = e;
                             const int bl = logblock - jrc;           // block >> jrc = 2^bl samples
                             if (((m + 1) & ((1 << bl) - 1)) == 0)
-                                sEN[((((m + 1) >> bl) - 1) & (EN_RING - 1)) * 32 + (n_oct - 1 - jrc) * BPO + r] =
+                                sEN[((((m + 1) >> bl) - 1) & (EN_RING - 1)) * 32 + (n_oct - 1 - jrc) * BPO + band] =
                                     v_mul(alj * gb_lane * gb_lane, e);
                         }
                     }
@@ -435,48 +460,50 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
         const bool ge = opq(G != 0);
         if (ge && pvc) {
 #pragma unroll
-            for (int e = 0; e < 4; e++) spc[e] = cur[e];
+            for (int e = 0; e < RS; e++) spc[e] = cur[e];
         }
 #pragma unroll
-        for (int e = 0; e < 4; e++) zc[e] = v_sel(!ge && pv0, cur[e], zc[e]);
+        for (int e = 0; e < RS; e++) zc[e] = v_sel(!ge && pv0, cur[e], zc[e]);
     };
 
     // ================================================================ phase B: smoothing, prefetch
     auto phaseB = [&](int k, auto check_tag) {
         constexpr bool CHECK = decltype(check_tag)::value;
-        const bool valid0 = !CHECK || (unsigned)k < (unsigned)n_chunks;
+        const int kb = k - BSK;        // the stage-0 chunk whose band outputs were written in this step
+        const bool valid0 = !CHECK || (unsigned)kb < (unsigned)n_chunks;
         bool vm[NSL];
 #pragma unroll
         for (int q = 0; q < NSL; q++) {
             vm[q] = mok[q];
-            if (CHECK) vm[q] = vm[q] && (unsigned)(k - DEC_DEPTH * mst[q]) < (unsigned)n_chunks;
+            if (CHECK) vm[q] = vm[q] && (unsigned)(kb - DEC_DEPTH * mst[q]) < (unsigned)n_chunks;
         }
 #pragma unroll
         for (int b = 0; b < BPO; b++) {
-            const T *y0p = sW + b * LY::WSTR + (k & 1) * CH;            // band b of group 0 / group 1
-            const T *ymp = sW + (NR + b) * LY::WSTR + (k & 1) * CH;
+            constexpr int OL = SPL == 2 ? 1 : 2;                           // band b's output lane: OL*b + OL-1
+            const T *y0p = sW + (OL * b + OL - 1) * LY::WSTR + (k & 1) * CH;            // group 0 / group 1
+            const T *ymp = sW + (NR + OL * b + OL - 1) * LY::WSTR + (k & 1) * CH;
             // raw units of the normalised sections; the squared chain gain is applied on emission
 #pragma unroll
             for (int q = 0; q < NSL; q++) {
-                const int p = hl + 16 * q;
+                const int p = hl + HW * q;
                 if (valid0) acc0[b][q] = v_add(v_fma(-P.aq0, acc0[b][q], acc0[b][q]), v_sq(y0p[p]));
                 if (vm[q]) accm[b][q] = v_add(v_fma(-aqm[q], accm[b][q], accm[b][q]), v_sq(ymp[p]));
             }
         }
         // ---- block ends (warp-uniform conditions: they depend on the step only)
-        if (valid0 && (((k + 1) & nbmask) == 0)) {     // stage 0: weighted sum of its CH accumulators
-            const int blk = ((k + 1) >> lognb) - 1;
+        if (valid0 && (((kb + 1) & nbmask) == 0)) {    // stage 0: weighted sum of its CH accumulators
+            const int blk = ((kb + 1) >> lognb) - 1;
 #pragma unroll
             for (int b = 0; b < BPO; b++) {
                 T val = v_fma(-om0[0], acc0[b][0], acc0[b][0]);
 #pragma unroll
                 for (int q = 1; q < NSL; q++) val = v_add(val, v_fma(-om0[q], acc0[b][q], acc0[b][q]));
 #pragma unroll
-                for (int dlt = 8; dlt >= 1; dlt >>= 1) val = v_add(val, v_shfl_xor(val, dlt));
+                for (int dlt = HW / 2; dlt >= 1; dlt >>= 1) val = v_add(val, v_shfl_xor(val, dlt));
 #pragma unroll
                 for (int q = 0; q < NSL; q++) {
                     v_set(acc0[b][q], 0.f, 0.f);
-                    if (hl + 16 * q == CH - 1) acc0[b][q] = val;
+                    if (hl + HW * q == CH - 1) acc0[b][q] = val;
                 }
                 if (hl == 0)
                     sEN[(blk & (EN_RING - 1)) * 32 + (n_oct - 1) * BPO + b] = v_mul(P.alpha[0] * P.gband[b] * P.gband[b], val);
@@ -484,35 +511,35 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
         }
 #pragma unroll
         for (int j = 1; j <= LOGCH; j++) {             // chunked lower-rate stages
-            const int cm = k - DEC_DEPTH * j;
+            const int cm = kb - DEC_DEPTH * j;
             const bool ev = j <= n_oct - 1 && (unsigned)cm < (unsigned)n_chunks && (((cm + 1) & nbmask) == 0);
             if (!ev) continue;
             const int blk = ((cm + 1) >> lognb) - 1;
             const int len = CH >> j, lo = CH - 2 * len;          // slots [lo, lo + len)
             const int kb0 = (n_oct - 1 - j) * BPO;
-            if (len >= 16) {
-                // the stage fills whole registers q in [lo/16, (lo+len)/16): every lane takes part
+            if (len >= HW) {
+                // the stage fills whole registers q in [lo/HW, (lo+len)/HW): every lane takes part
 #pragma unroll
                 for (int b = 0; b < BPO; b++) {
                     T val;
                     v_set(val, 0.f, 0.f);
 #pragma unroll
-                    for (int q = lo / 16; q < (lo + len) / 16; q++)
+                    for (int q = lo / HW; q < (lo + len) / HW; q++)
                         val = v_add(val, v_fma(-omm[q], accm[b][q], accm[b][q]));
 #pragma unroll
-                    for (int dlt = 8; dlt >= 1; dlt >>= 1) val = v_add(val, v_shfl_xor(val, dlt));
+                    for (int dlt = HW / 2; dlt >= 1; dlt >>= 1) val = v_add(val, v_shfl_xor(val, dlt));
 #pragma unroll
-                    for (int q = lo / 16; q < (lo + len) / 16; q++) {
+                    for (int q = lo / HW; q < (lo + len) / HW; q++) {
                         v_set(accm[b][q], 0.f, 0.f);
-                        if (hl + 16 * q == lo + len - 1) accm[b][q] = val;
+                        if (hl + HW * q == lo + len - 1) accm[b][q] = val;
                     }
                     if (hl == 0)
                         sEN[(blk & (EN_RING - 1)) * 32 + kb0 + b] = v_mul(sAl[j] * P.gband[b] * P.gband[b], val);
                 }
             } else {
-                // the stage sits in lanes [lo & 15, (lo & 15) + len) of the last register
+                // the stage sits in lanes [lo % HW, lo % HW + len) of the last register
                 constexpr int q = NSL - 1;
-                const int l0 = lo & 15;
+                const int l0 = lo & (HW - 1);
                 const bool mine = hl >= l0 && hl < l0 + len;
 #pragma unroll
                 for (int b = 0; b < BPO; b++) {
@@ -520,7 +547,7 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
                     v_set(val, 0.f, 0.f);
                     if (mine) val = v_fma(-omm[q], accm[b][q], accm[b][q]);
 #pragma unroll
-                    for (int dlt = 1; dlt < 8; dlt <<= 1) {
+                    for (int dlt = 1; dlt < HW / 2; dlt <<= 1) {
                         if (dlt < len) val = v_add(val, v_shfl_xor(val, dlt));
                     }
                     if (mine) {
@@ -539,7 +566,7 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
                 __syncwarp();
                 if (want_e) {
                     const int blk = (kf >> lognb) - 1;
-                    for (int i = hl; i < nbands; i += 16) {
+                    for (int i = hl; i < nbands; i += HW) {
                         const T v = sEN[(blk & (EN_RING - 1)) * 32 + i];
                         float e0 = v_x(v), e1 = v_y(v);
                         if (a.db) {     // friture/octavespectrum.py:119-121: 10*log10(sp + 1e-30) + w
@@ -573,18 +600,18 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
     // ---- epilogue: the pipeline is drained, every stage ended on a block boundary
     if (worker && !G) {
 #pragma unroll
-        for (int i = 0; i < 4; i++) sS[r * 4 + i] = zc[i];
+        for (int i = 0; i < RS; i++) sS[r * RS + i] = zc[i];
     }
     __syncwarp();
     if (alive) {
-        for (int i = hl; i < n_oct * NSEC * 2; i += 16) {
+        for (int i = hl; i < n_oct * NSEC * 2; i += HW) {
             const T z = sS[i];
             gz0[i] = v_x(z);
             if (has2) gz1[i] = v_y(z);
         }
 #pragma unroll
         for (int q = 0; q < NSL; q++) {
-            const int p = hl + 16 * q;
+            const int p = hl + HW * q;
 #pragma unroll
             for (int b = 0; b < BPO; b++) {
                 if (p == CH - 1) {
@@ -597,7 +624,7 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
                 }
             }
         }
-        for (int i = hl; i < (n_oct - JR) * BPO; i += 16) {     // ruler stages
+        for (int i = hl; i < (n_oct - JR) * BPO; i += HW) {     // ruler stages
             const int j = JR + i / BPO, b = i % BPO;
             const T e = sER[j * 4 + b];
             ge0[j * BPO + b] = v_x(e);
@@ -606,23 +633,28 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
     }
 }
 
-template <int LOGCH, int PACK, int BPO>
+template <int LOGCH, int PACK, int BPO, int SPL>
 cudaError_t launch_pipe(const PipeParams &P, const BankArgs &a, cudaStream_t st) {
-    using LY = PipeLayout<LOGCH, PACK, BPO>;
-    const size_t smem = (size_t)LY::TB * 2 * LY::TOTAL + 2 * 12 * 4;
-    auto kern = bank_pipe_kernel<LOGCH, PACK, BPO>;
+    using LY = PipeLayout<LOGCH, PACK, BPO, SPL>;
+    const size_t smem = (size_t)LY::TB * Geo<SPL>::NSLOT * LY::TOTAL + 2 * 12 * 4;
+    auto kern = bank_pipe_kernel<LOGCH, PACK, BPO, SPL>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const int per_warp = 2 * PACK;
+    const int per_warp = Geo<SPL>::NSLOT * PACK;
     const unsigned blocks = (unsigned)((a.n_channels + per_warp - 1) / per_warp);
     kern<<<blocks, 32, smem, st>>>(P, a);
     return cudaGetLastError();
 }
 
-template <int LOGCH, int PACK>
+template <int LOGCH, int PACK, int SPL>
 cudaError_t launch_pipe_bpo(const PipeParams &P, const BankArgs &a, cudaStream_t st) {
-    if (P.bpo == 3) return launch_pipe<LOGCH, PACK, 3>(P, a, st);
-    return launch_pipe<LOGCH, PACK, 1>(P, a, st);
+    if (P.bpo == 3) return launch_pipe<LOGCH, PACK, 3, SPL>(P, a, st);
+    return launch_pipe<LOGCH, PACK, 1, SPL>(P, a, st);
+}
+template <int LOGCH, int PACK>
+cudaError_t launch_pipe_spl(const PipeParams &P, const BankArgs &a, int spl, cudaStream_t st) {
+    if (spl == 1) return launch_pipe_bpo<LOGCH, PACK, 1>(P, a, st);
+    return launch_pipe_bpo<LOGCH, PACK, 2>(P, a, st);
 }
 
 }   // namespace
@@ -632,7 +664,8 @@ cudaError_t launch_pipe_bpo(const PipeParams &P, const BankArgs &a, cudaStream_t
 // per step, DEC_DEPTH steps (the decimator chain) behind the previous stage; stage j > logch has one
 // sample every P_j = 2^(j-logch) steps, at steps u = T_j (mod P_j) with T_j = P_j/2 - 1 (mod P_j),
 // which makes the stages' turns disjoint (the ruler sequence JR + ctz(u+1)).
-void frt_pipe_schedule(int n_oct, int logch, long long t_total, int *T, int *n_steps) {
+void frt_pipe_schedule(int n_oct, int logch, int spl, long long t_total, int *T, int *n_steps) {
+    const int DEC_DEPTH = spl == 1 ? Geo<1>::DD : Geo<2>::DD, BSK = spl == 1 ? Geo<1>::BSK : Geo<2>::BSK;
     T[0] = 0;
     for (int j = 1; j <= BANK_MAX_OCT; j++) {
         int t = T[j - 1] + DEC_DEPTH;
@@ -646,14 +679,14 @@ void frt_pipe_schedule(int n_oct, int logch, long long t_total, int *T, int *n_s
     const long long n_chunks = t_total >> logch;
     long long last = 0;
     for (int j = 0; j < n_oct; j++) {
-        const int dmax = (j == n_oct - 1) ? 0 : DEC_DEPTH - 1;
+        const int dmax = (j == n_oct - 1) ? BSK : DEC_DEPTH - 1;
         long long l;
         if (j <= logch) l = n_chunks - 1 + T[j] + dmax;
         else l = T[j] + (((t_total >> j) - 1) << (j - logch)) + dmax;
         if (l > last) last = l;
     }
     // block b's band vector is flushed at step (b+1)*NB - 1 + delta
-    const long long flush_last = n_chunks - 1 + frt_pipe_flush_delta(n_oct, logch, T);
+    const long long flush_last = n_chunks - 1 + frt_pipe_flush_delta(n_oct, logch, spl, T);
     if (flush_last > last) last = flush_last;
     *n_steps = (int)(last + 1);
 }
@@ -661,21 +694,21 @@ void frt_pipe_schedule(int n_oct, int logch, long long t_total, int *T, int *n_s
 // Steps after a block's last stage-0 chunk (step (b+1)*NB - 1) at which every stage has staged the
 // block's band energies: chunked stage j reports T_j steps later, ruler stage j during step
 // T_j - P_j of that scale (readable one phase later, hence + 1).
-int frt_pipe_flush_delta(int n_oct, int logch, const int *T) {
+int frt_pipe_flush_delta(int n_oct, int logch, int spl, const int *T) {
     int delta = 0;
     for (int j = 1; j < n_oct; j++) {
         const int dj = j <= logch ? T[j] : T[j] - (1 << (j - logch)) + 1;
         if (dj > delta) delta = dj;
     }
-    return delta;
+    return delta + (spl == 1 ? Geo<1>::BSK : Geo<2>::BSK);     // band outputs trail by BSK steps
 }
 
 void frt_pipe_prepare(BankPlan *pl) {
     const BankParams &B = pl->params;
     pl->pipe_ok = (B.bpo == 1 || B.bpo == 3);
     if (!pl->pipe_ok) return;
-    for (int v = 0; v < 2; v++) {
-        const int logch = 5 + v, CH = 1 << logch;
+    for (int v = 0; v < 4; v++) {
+        const int logch = 5 + (v >> 1), CH = 1 << logch, spl = 2 - (v & 1);
         PipeParams &P = pl->pipe[v];
         memset(&P, 0, sizeof(P));
         P.n_oct = B.n_oct;
@@ -688,8 +721,8 @@ void frt_pipe_prepare(BankPlan *pl) {
         for (int b = 0; b < B.bpo; b++) P.gband[b] = B.gband[b];
         P.gdec = B.gdec;
         for (int j = 0; j <= BANK_MAX_OCT; j++) P.alpha[j] = j < B.n_oct ? (float)pl->alphas[j] : 1.f;
-        frt_pipe_schedule(B.n_oct, logch, 0, P.T, nullptr);
-        P.fdelta = frt_pipe_flush_delta(B.n_oct, logch, P.T);
+        frt_pipe_schedule(B.n_oct, logch, spl, 0, P.T, nullptr);
+        P.fdelta = frt_pipe_flush_delta(B.n_oct, logch, spl, P.T);
         const double q0 = 1.0 - pl->alphas[0];
         P.aq0 = (float)(1.0 - pow(q0, CH));
         for (int p = 0; p < CH; p++) {
@@ -706,10 +739,22 @@ void frt_pipe_prepare(BankPlan *pl) {
     }
 }
 
-cudaError_t frt_pipe_launch(const BankPlan *pl, BankArgs a, int logch, int pack, cudaStream_t st) {
-    const PipeParams &P = pl->pipe[logch - 5];
+bool frt_pipe_supported(const BankPlan *pl, int block, int logch, int spl) {
+    if (!pl->pipe_ok || (block & (block - 1)) || block < (4 << logch)) return false;
+    const PipeParams &P = pl->pipe[2 * (logch - 5) + (2 - spl)];
+    if ((block >> (P.n_oct - 1)) < 1) return false;
+    const int nb = block >> logch;                      // steps per block
+    const int ring = spl == 1 ? EnRing<1>::N : EnRing<2>::N;
+    // blocks staged but not yet flushed when a block's vector leaves, plus the one being written
+    return (P.fdelta + nb - 1) / nb + 1 <= ring;
+}
+
+cudaError_t frt_pipe_launch(const BankPlan *pl, BankArgs a, int logch, int pack, int spl, cudaStream_t st) {
+    if (!frt_pipe_supported(pl, a.block, logch, spl)) return cudaErrorInvalidConfiguration;
+    const PipeParams &P = pl->pipe[2 * (logch - 5) + (2 - spl)];
     int T[BANK_MAX_OCT + 1];
-    frt_pipe_schedule(P.n_oct, logch, a.t_total, T, &a.n_steps);
-    if (logch == 5) return pack == 2 ? launch_pipe_bpo<5, 2>(P, a, st) : launch_pipe_bpo<5, 1>(P, a, st);
-    return pack == 2 ? launch_pipe_bpo<6, 2>(P, a, st) : launch_pipe_bpo<6, 1>(P, a, st);
+    frt_pipe_schedule(P.n_oct, logch, spl, a.t_total, T, &a.n_steps);
+    if (logch == 5)
+        return pack == 2 ? launch_pipe_spl<5, 2>(P, a, spl, st) : launch_pipe_spl<5, 1>(P, a, spl, st);
+    return pack == 2 ? launch_pipe_spl<6, 2>(P, a, spl, st) : launch_pipe_spl<6, 1>(P, a, spl, st);
 }

@@ -15,8 +15,11 @@
 //   lane (32-t)%32 and is fetched with warp shuffles.  Only __syncwarp(), no block barrier.
 //   Complex arithmetic is written on float2 so ptxas emits packed FADD2/FMUL2/FFMA2 (one issue
 //   slot per complex add, two per complex multiply).
-// Generic path (every other size 32..16384): one CTA per frame, Stockham radix-4 (+ one radix-2
-//   pass when log2(M) is odd) ping-ponging between two shared-memory buffers.
+// N = 64 .. 1024: one warp per 32/Q frames (N = 64 Q), the same two register passes (stft_small_kernel).
+// N = 4096 / 8192: R = 2 / 4 warps per frame, each a 1024-point FFT of a decimated sequence, radix-R
+//   combine through shared memory (stft_large_kernel; stft_multi_kernel for unaligned input and 16384).
+// Generic path (N = 32): one CTA per frame, Stockham radix-4 (+ one radix-2 pass when log2(M) is
+//   odd) ping-ponging between two shared-memory buffers.
 #include <cmath>
 #include <cstdlib>
 
@@ -145,6 +148,40 @@ __device__ __forceinline__ void dft32(float2 (&v)[32]) {
             }
         }
     }
+}
+
+// 32/LEN independent LEN-point DFTs on consecutive register groups (same butterflies as dft32,
+// started at span LEN): v[g*LEN + r] <- bin brevq<LEN>(r) of group g.
+template <int LEN>
+__device__ __forceinline__ void dft_groups(float2 (&v)[32]) {
+#pragma unroll
+    for (int len = LEN; len >= 2; len >>= 1) {
+        const int half = len >> 1;
+        const int tstep = 32 / len;
+#pragma unroll
+        for (int base = 0; base < 32; base += len) {
+#pragma unroll
+            for (int i = 0; i < half; i++) {
+                const float2 a = v[base + i], b = v[base + i + half];
+                v[base + i] = cadd(a, b);
+                const float2 d = csub(a, b);
+                const int ti = i * tstep;
+                if (ti == 0)
+                    v[base + i + half] = d;
+                else if (ti == 8)
+                    v[base + i + half] = mul_mj(d);
+                else
+                    v[base + i + half] = cmul(d, make_float2(cos32(ti), -sin32(ti)));
+            }
+        }
+    }
+}
+template <int Q>
+__host__ __device__ constexpr int brevq(int r) {
+    int o = 0;
+    for (int b = 1, c = Q >> 1; b < Q; b <<= 1, c >>= 1)
+        if (r & b) o |= c;
+    return o;
 }
 
 __device__ __forceinline__ float lg2_fast(float v) {
@@ -508,6 +545,307 @@ stft_multi_kernel(const float *__restrict__ x, long long x_stride, long long n_f
 }
 
 // ------------------------------------------------------------------------------------------
+// N = 64 Q, Q in {1, 2, 4, 8, 16} (64 .. 1024 points): ONE WARP PER G = 32/Q FRAMES.
+// M = N/2 = 32 Q.  Lane t holds z_g[32 n1 + t] (n1 < Q) of each of the G frames in register g*Q + n1,
+// so the register file is as full as in the N = 2048 kernel: G radix-Q DFTs in registers -> twiddle
+// W_M^(k1 t) -> ONE 32x32 transpose through the warp's tile, after which lane g*Q + k1 holds the 32
+// values (over t) of frame g, residue k1 -> radix-32 DFT -> that lane owns Z_g[k1 + Q k2], k2 = 0..31.
+// The split partner M - (k1 + Q m) = (Q - k1) + Q (31 - m) lives in lane g*Q + (Q - k1) % Q (the
+// lane itself when k1 = 0), one shuffle away.  Window, twiddle and split tables are read once per
+// G frames.
+constexpr int SMALL_WARPS = 8;
+template <int Q>
+constexpr size_t small_smem() {
+    return sizeof(float2) * (32 * Q + 32 * Q + 16 * Q + (size_t)SMALL_WARPS * FAST_TILE);
+}
+
+template <int Q, int MODE>
+__global__ void __launch_bounds__(SMALL_WARPS * 32, 2)
+stft_small_kernel(const float *__restrict__ x, long long x_stride, long long n_frames, int hop,
+                  float *__restrict__ out, long long out_stride_c, long long out_stride_f,
+                  const float2 *__restrict__ win2, const float2 *__restrict__ tw,
+                  const float2 *__restrict__ post, long long total_items, int vec_ok) {
+    constexpr int G = 32 / Q, M = 32 * Q, N = 2 * M;
+    extern __shared__ float2 smem[];
+    float2 *s_win = smem;              // [M]     (w[2n], w[2n+1])
+    float2 *s_tw = s_win + M;          // [Q][32] W_M^(k1 t)
+    float2 *s_post = s_tw + M;         // [M/2]   U[k] = -j W_N^k
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float2 *s_x = s_post + 16 * Q + warp * FAST_TILE;
+    for (int i = threadIdx.x; i < M; i += blockDim.x) {
+        s_win[i] = win2[i];
+        s_tw[i] = tw[i];
+    }
+    for (int i = threadIdx.x; i < 16 * Q; i += blockDim.x) s_post[i] = post[i];
+    __syncthreads();
+
+    // contiguous range of frames per warp, a multiple of G long
+    const long long warps_total = (long long)gridDim.x * SMALL_WARPS;
+    const long long gw = (long long)blockIdx.x * SMALL_WARPS + warp;
+    long long per = (total_items + warps_total - 1) / warps_total;
+    per = (per + G - 1) / G * G;
+    long long item = gw * per;
+    long long item_end = item + per;
+    if (item_end > total_items) item_end = total_items;
+    const float scale = 1.0f / (4.0f * (float)N * (float)N);
+    const int k1 = lane & (Q - 1), gsel = lane / Q;
+    const int src_lane = (lane - k1) + ((Q - k1) & (Q - 1));
+
+    long long c = (item < item_end) ? item / n_frames : 0;
+    long long f = item - c * n_frames;
+    for (; item < item_end; item += G) {
+        float2 v[32];
+        long long myc = 0, myf = 0;
+        bool myok = false;
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            const bool ok = item + g < item_end;
+            const float *p = x + c * x_stride + f * hop;
+            if (g == gsel) {
+                myc = c;
+                myf = f;
+                myok = ok;
+            }
+            if (ok && vec_ok) {
+#pragma unroll
+                for (int n1 = 0; n1 < Q; n1++)
+                    v[g * Q + n1] = __ldg(reinterpret_cast<const float2 *>(p) + 32 * n1 + lane);
+            } else if (ok) {
+#pragma unroll
+                for (int n1 = 0; n1 < Q; n1++) {
+                    v[g * Q + n1].x = __ldg(p + 64 * n1 + 2 * lane);
+                    v[g * Q + n1].y = __ldg(p + 64 * n1 + 2 * lane + 1);
+                }
+            } else {
+#pragma unroll
+                for (int n1 = 0; n1 < Q; n1++) v[g * Q + n1] = make_float2(0.0f, 0.0f);
+            }
+            if (++f == n_frames) {
+                f = 0;
+                c++;
+            }
+        }
+#pragma unroll
+        for (int n1 = 0; n1 < Q; n1++) {
+            const float2 w = s_win[32 * n1 + lane];
+#pragma unroll
+            for (int g = 0; g < G; g++) v[g * Q + n1] = __fmul2_rn(v[g * Q + n1], w);
+        }
+        dft_groups<Q>(v);   // v[g*Q + r] = sum_n1 z_g[32 n1 + t] W_Q^(n1 k1), k1 = brevq<Q>(r)
+#pragma unroll
+        for (int r = 0; r < Q; r++) {
+            const int kk1 = brevq<Q>(r);
+            const float2 w = s_tw[kk1 * 32 + lane];
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                const float2 val = (kk1 == 0) ? v[g * Q + r] : cmul(v[g * Q + r], w);
+                s_x[(g * Q + kk1) * 33 + lane] = val;
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int n2 = 0; n2 < 32; n2++) v[n2] = s_x[lane * 33 + n2];
+        __syncwarp();
+        dft32(v);   // v[r] = Z_g[k1 + Q*brev5(r)] of this lane's (g, k1)
+
+        float *o = out + myc * out_stride_c + myf * out_stride_f;
+#pragma unroll
+        for (int m = 0; m < 16; m++) {
+            const float2 z = v[brev5(m)];
+            const float2 other = v[brev5(31 - m)];
+            float2 zp;
+            zp.x = __shfl_sync(0xffffffffu, other.x, src_lane);
+            zp.y = __shfl_sync(0xffffffffu, other.y, src_lane);
+            if (k1 == 0) zp = (m == 0) ? v[0] : v[brev5(32 - m)];
+            const float2 E = make_float2(z.x + zp.x, z.y - zp.y);
+            const float2 O = make_float2(z.x - zp.x, z.y + zp.y);
+            const int k = k1 + Q * m;
+            const float2 T = cmul(O, s_post[k]);
+            const float2 X = cadd(E, T);
+            const float2 Y = csub(E, T);
+            const float p1 = fmaf(X.x, X.x, X.y * X.y);
+            const float p2 = fmaf(Y.x, Y.x, Y.y * Y.y);
+            if (myok) {
+                o[k] = finish<MODE>(p1, scale);
+                o[M - k] = finish<MODE>(p2, scale);
+            }
+        }
+        if (k1 == 0 && myok) {
+            const float2 z = v[brev5(16)];   // bin M/2: X = conj(Z)
+            o[M / 2] = finish<MODE>(4.0f * fmaf(z.x, z.x, z.y * z.y), scale);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// N = 4096 / 8192, 8-byte aligned input: the stft_multi_kernel decomposition (R warps per frame, each a
+// 1024-point complex FFT of a decimated sequence, then a radix-R combine + split step) rebuilt
+// around shared memory: one CTA of 16 warps (16/R frame groups) per SM, every table resident in shared
+// memory, the frame fetched by 8-byte cp.async that DE-INTERLEAVES it on the way in (element e of the
+// frame lands in warp e % R's tile at e / R, staggered by w*32/R so that the scatter is conflict
+// free), named barriers per group instead of block barriers.
+// The Hann window is computed on the fly (this kernel is bound by shared-memory wavefronts, not by
+// the FMA pipe): w[n] = 0.5 - 0.5 cos(theta n), theta = 2 pi/(N-1), and for warp w, lane t, register
+// n1, element e the sample index is n = 64 R n1 + (2 R t + 2 w + e) = A-part + B-part, so
+// cos(theta n) = cos A cos B - sin A sin B with 32 (cos A, sin A)/2 pairs passed as a kernel
+// argument (constant bank) and the four B factors of a lane held in registers.
+constexpr int LARGE_WARPS = 16;
+struct HannA {
+    float2 v[32];     // (0.5 cos(theta 64 R n1), 0.5 sin(theta 64 R n1))
+};
+template <int R>
+constexpr size_t large_smem() {
+    // tw [1024] + comb [R-1][1024] + post [512 R + 1 -> even] + tiles
+    return sizeof(float2) * (1024 + 1024 * (R - 1) + 512 * R + 2 + (size_t)LARGE_WARPS * FAST_TILE);
+}
+
+__device__ __forceinline__ void group_barrier(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *dst_smem, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+// split twiddle U[kk] = -j W_N^kk for kk in [0, M] from a table of M/2 + 1 entries:
+// U[kk + M/2] = -j U[kk]
+__device__ __forceinline__ float2 post_lookup(const float2 *s_post, int kk, int half_m) {
+    if (kk <= half_m) return s_post[kk];
+    return mul_mj(s_post[kk - half_m]);
+}
+
+template <int R, int MODE>
+__device__ __forceinline__ void split_store_s(float *__restrict__ o, int kk, float2 z, float2 zp,
+                                              const float2 *s_post, float scale) {
+    constexpr int M = 1024 * R;
+    const float2 E = make_float2(z.x + zp.x, z.y - zp.y);
+    const float2 O = make_float2(z.x - zp.x, z.y + zp.y);
+    const float2 T = cmul(O, post_lookup(s_post, kk, M / 2));
+    const float2 X = cadd(E, T);
+    const float2 Y = csub(E, T);
+    o[kk] = finish<MODE>(fmaf(X.x, X.x, X.y * X.y), scale);
+    o[M - kk] = finish<MODE>(fmaf(Y.x, Y.x, Y.y * Y.y), scale);
+}
+
+template <int R>
+__device__ __forceinline__ void load_group_s(const float2 *tiles, const float2 *s_comb, int k0,
+                                             float2 (&t)[R]) {
+    t[0] = tiles[k0];
+#pragma unroll
+    for (int w = 1; w < R; w++) t[w] = cmul(tiles[w * FAST_TILE + k0], s_comb[(w - 1) * 1024 + k0]);
+    combine<R>(t);
+}
+
+template <int R, int MODE>
+__global__ void __launch_bounds__(LARGE_WARPS * 32, 1)
+stft_large_kernel(const float *__restrict__ x, long long x_stride, long long n_frames, int hop,
+                  float *__restrict__ out, long long out_stride_c, long long out_stride_f,
+                  const float4 *__restrict__ wlane, const float2 *__restrict__ tw32,
+                  const float2 *__restrict__ comb, const float2 *__restrict__ post,
+                  long long total_items, const __grid_constant__ HannA hann_a) {
+    // STAG: 8-byte shared accesses are served per half-warp; the 16/R elements a half-warp sends to
+    // each of the R tiles must fall on different banks
+    constexpr int M = 1024 * R, N = 2 * M, NG = LARGE_WARPS / R, GT = 32 * R, STAG = 16 / R;
+    extern __shared__ float2 smem[];
+    float2 *s_tw = smem;                          // [32][32] W_1024^(k1 t)
+    float2 *s_comb = s_tw + 1024;                 // [R-1][1024] W_M^(w k0)
+    float2 *s_post = s_comb + 1024 * (R - 1);     // [M/2 + 1] U[k]
+    float2 *s_tiles_all = s_post + 512 * R + 2;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int grp = warp / R, w = warp % R, gtid = tid - grp * GT;
+    float2 *s_tiles = s_tiles_all + (size_t)grp * R * FAST_TILE;   // this group's R tiles
+    float2 *s_x = s_tiles + w * FAST_TILE;
+    for (int i = tid; i < 1024; i += blockDim.x) s_tw[i] = tw32[i];
+    for (int i = tid; i < 1024 * (R - 1); i += blockDim.x) s_comb[i] = comb[i];
+    for (int i = tid; i <= 512 * R; i += blockDim.x) s_post[i] = post[i];
+    __syncthreads();
+
+    const long long groups_total = (long long)gridDim.x * NG;
+    const long long gg = (long long)blockIdx.x * NG + grp;
+    const long long per = (total_items + groups_total - 1) / groups_total;
+    long long item = gg * per;
+    long long item_end = item + per;
+    if (item_end > total_items) item_end = total_items;
+    const float scale = 1.0f / (4.0f * (float)N * (float)N);
+    long long c = (item < item_end) ? item / n_frames : 0;
+    long long f = item - c * n_frames;
+    const float4 wb = wlane[w * 32 + lane];       // cos B (e = 0, 1), sin B (e = 0, 1)
+    const float2 wcb = make_float2(wb.x, wb.y), wsb = make_float2(wb.z, wb.w);
+
+    auto fetch = [&](long long cc, long long ff) {
+        const float2 *p2 = reinterpret_cast<const float2 *>(x + cc * x_stride + ff * hop);
+#pragma unroll 8
+        for (int e = gtid; e < M; e += GT) {
+            const int ww = e % R, i = e / R;
+            cp_async8(s_tiles + ww * FAST_TILE + ww * STAG + i, p2 + e);
+        }
+    };
+    if (item < item_end) fetch(c, f);
+    for (; item < item_end; item++) {
+        cp_async_commit_wait_all();
+        group_barrier(1 + grp, GT);          // the whole frame has landed
+        float2 v[32];
+#pragma unroll
+        for (int n1 = 0; n1 < 32; n1++) v[n1] = s_x[w * STAG + 32 * n1 + lane];
+        __syncwarp();                        // inputs are in registers: the tile becomes the exchange buffer
+#pragma unroll
+        for (int n1 = 0; n1 < 32; n1++) {
+            const float ca = hann_a.v[n1].x, sa = hann_a.v[n1].y;
+            float2 wv = __ffma2_rn(make_float2(-ca, -ca), wcb, make_float2(0.5f, 0.5f));
+            wv = __ffma2_rn(make_float2(sa, sa), wsb, wv);
+            v[n1] = __fmul2_rn(v[n1], wv);
+        }
+        dft32(v);
+#pragma unroll
+        for (int r = 0; r < 32; r++) {
+            const int k1 = brev5(r);
+            const float2 val = (k1 == 0) ? v[r] : cmul(v[r], s_tw[k1 * 32 + lane]);
+            s_x[k1 * 33 + lane] = val;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int n2 = 0; n2 < 32; n2++) v[n2] = s_x[lane * 33 + n2];
+        __syncwarp();
+        dft32(v);   // v[r] = Z_w[lane + 32*brev5(r)]
+#pragma unroll
+        for (int r = 0; r < 32; r++) s_x[lane + 32 * brev5(r)] = v[r];   // natural order
+        group_barrier(1 + grp, GT);
+
+        float *o = out + c * out_stride_c + f * out_stride_f;
+        for (int k0 = 1 + gtid; k0 < 512; k0 += GT) {
+            float2 A[R], B[R];
+            load_group_s<R>(s_tiles, s_comb, k0, A);
+            load_group_s<R>(s_tiles, s_comb, 1024 - k0, B);
+#pragma unroll
+            for (int q = 0; q < R; q++)
+                split_store_s<R, MODE>(o, k0 + 1024 * q, A[q], B[R - 1 - q], s_post, scale);
+        }
+        if (gtid == 0) {           // k0 = 0: partners inside the group, q <-> R - q
+            float2 A[R];
+            load_group_s<R>(s_tiles, s_comb, 0, A);
+            split_store_s<R, MODE>(o, 0, A[0], A[0], s_post, scale);
+#pragma unroll
+            for (int q = 1; q <= R / 2; q++) split_store_s<R, MODE>(o, 1024 * q, A[q], A[R - q], s_post, scale);
+        }
+        if (gtid == 32) {          // k0 = 512: partners inside the group, q <-> R - 1 - q
+            float2 A[R];
+            load_group_s<R>(s_tiles, s_comb, 512, A);
+#pragma unroll
+            for (int q = 0; q < R / 2; q++)
+                split_store_s<R, MODE>(o, 512 + 1024 * q, A[q], A[R - 1 - q], s_post, scale);
+        }
+        if (++f == n_frames) {
+            f = 0;
+            c++;
+        }
+        group_barrier(1 + grp, GT);          // every Z_w has been read: the tiles are free again
+        if (item + 1 < item_end) fetch(c, f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Generic path: one CTA per frame, Stockham autosort in shared memory.
 __device__ __forceinline__ void stockham_radix4(const float2 *__restrict__ in,
                                                 float2 *__restrict__ outb,
@@ -620,6 +958,56 @@ void launch_fast(unsigned blocks, cudaStream_t st, const float *x, long long x_s
         pl.tw_dev, pl.post_dev, pl.wlane_dev, total);
 }
 
+template <int Q>
+cudaError_t set_small_smem() {
+    cudaError_t e = cudaFuncSetAttribute(stft_small_kernel<Q, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)small_smem<Q>());
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(stft_small_kernel<Q, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)small_smem<Q>());
+    return e;
+}
+template <int R>
+cudaError_t set_large_smem() {
+    cudaError_t e = cudaFuncSetAttribute(stft_large_kernel<R, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)large_smem<R>());
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(stft_large_kernel<R, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)large_smem<R>());
+    return e;
+}
+
+template <int Q>
+void launch_small(int mode, unsigned blocks, cudaStream_t st, const float *x, long long x_stride,
+                  long long n_frames, int hop, float *out, long long osc, long long osf,
+                  const StftPlan &pl, long long total, int vec_ok) {
+    const float2 *w2 = reinterpret_cast<const float2 *>(pl.win_dev);
+    if (mode == FRT_STFT_POWER)
+        stft_small_kernel<Q, FRT_STFT_POWER><<<blocks, SMALL_WARPS * 32, small_smem<Q>(), st>>>(
+            x, x_stride, n_frames, hop, out, osc, osf, w2, pl.tw_dev, pl.post_dev, total, vec_ok);
+    else
+        stft_small_kernel<Q, FRT_STFT_LOGPOWER><<<blocks, SMALL_WARPS * 32, small_smem<Q>(), st>>>(
+            x, x_stride, n_frames, hop, out, osc, osf, w2, pl.tw_dev, pl.post_dev, total, vec_ok);
+}
+template <int R>
+void launch_large(int mode, unsigned blocks, cudaStream_t st, const float *x, long long x_stride,
+                  long long n_frames, int hop, float *out, long long osc, long long osf,
+                  const StftPlan &pl, long long total) {
+    const float4 *wl = reinterpret_cast<const float4 *>(pl.wlane_dev);
+    HannA ha;
+    const double theta = 2.0 * 3.14159265358979323846 / (double)(2048 * R - 1);
+    for (int n1 = 0; n1 < 32; n1++) {
+        const double a = theta * 64.0 * R * n1;
+        ha.v[n1] = make_float2((float)(0.5 * cos(a)), (float)(0.5 * sin(a)));
+    }
+    if (mode == FRT_STFT_POWER)
+        stft_large_kernel<R, FRT_STFT_POWER><<<blocks, LARGE_WARPS * 32, large_smem<R>(), st>>>(
+            x, x_stride, n_frames, hop, out, osc, osf, wl, pl.tw_dev, pl.comb_dev, pl.post_dev, total, ha);
+    else
+        stft_large_kernel<R, FRT_STFT_LOGPOWER><<<blocks, LARGE_WARPS * 32, large_smem<R>(), st>>>(
+            x, x_stride, n_frames, hop, out, osc, osf, wl, pl.tw_dev, pl.comb_dev, pl.post_dev, total, ha);
+}
+
 size_t multi_smem(int r) { return sizeof(float2) * (FAST_M + (size_t)r * FAST_TILE); }
 
 int ilog2(int v) {
@@ -685,6 +1073,12 @@ extern "C" int frt_stft_plan(frt_handle h, int n_fft) {
                 const double a = -2.0 * PI * (double)((k1 * t) % M) / (double)M;
                 tw[k1 * 32 + t] = make_float2((float)cos(a), (float)sin(a));
             }
+    } else if (N >= 64 && N <= 1024) {   // stft_small_kernel: [Q][32] W_M^(k1 t), M = 32 Q
+        for (int k1 = 0; k1 < M / 32; k1++)
+            for (int t = 0; t < 32; t++) {
+                const double a = -2.0 * PI * (double)((k1 * t) % M) / (double)M;
+                tw[k1 * 32 + t] = make_float2((float)cos(a), (float)sin(a));
+            }
     } else {
         for (int i = 0; i < M; i++) {
             const double a = -2.0 * PI * (double)i / (double)M;
@@ -706,6 +1100,22 @@ extern "C" int frt_stft_plan(frt_handle h, int n_fft) {
         FRT_CUDA(h, cudaMemcpy(pl.wlane_dev, wl.data(), sizeof(float2) * 64,
                                cudaMemcpyHostToDevice));
     }
+    if (N == 4096 || N == 8192) {   // stft_large_kernel: per-(warp, lane) part of the Hann phase
+        const int R = N / 2048;
+        std::vector<float> wl((size_t)R * 32 * 4);
+        const double theta = 2.0 * PI / (double)(N - 1);
+        for (int w = 0; w < R; w++)
+            for (int t = 0; t < 32; t++) {
+                const double b0 = theta * (2 * R * t + 2 * w), b1 = theta * (2 * R * t + 2 * w + 1);
+                float *q = &wl[((size_t)w * 32 + t) * 4];
+                q[0] = (float)cos(b0);
+                q[1] = (float)cos(b1);
+                q[2] = (float)sin(b0);
+                q[3] = (float)sin(b1);
+            }
+        FRT_CUDA(h, cudaMalloc(&pl.wlane_dev, sizeof(float) * wl.size()));
+        FRT_CUDA(h, cudaMemcpy(pl.wlane_dev, wl.data(), sizeof(float) * wl.size(), cudaMemcpyHostToDevice));
+    }
     FRT_CUDA(h, cudaMalloc(&pl.win_dev, sizeof(float) * N));
     FRT_CUDA(h, cudaMalloc(&pl.tw_dev, sizeof(float2) * tw.size()));
     FRT_CUDA(h, cudaMalloc(&pl.post_dev, sizeof(float2) * post.size()));
@@ -724,6 +1134,14 @@ extern "C" int frt_stft_plan(frt_handle h, int n_fft) {
         FRT_CUDA(h, cudaFuncSetAttribute(stft_multi_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)multi_smem(4)));
         FRT_CUDA(h, cudaFuncSetAttribute(stft_multi_kernel<8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)multi_smem(8)));
         FRT_CUDA(h, cudaFuncSetAttribute(stft_multi_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)multi_smem(8)));
+        FRT_CUDA(h, set_large_smem<2>());
+        FRT_CUDA(h, set_large_smem<4>());
+    } else if (N >= 64 && N <= 1024) {
+        FRT_CUDA(h, set_small_smem<1>());
+        FRT_CUDA(h, set_small_smem<2>());
+        FRT_CUDA(h, set_small_smem<4>());
+        FRT_CUDA(h, set_small_smem<8>());
+        FRT_CUDA(h, set_small_smem<16>());
     } else {
         FRT_CUDA(h, cudaFuncSetAttribute(stft_generic_kernel,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -782,6 +1200,33 @@ extern "C" int frt_stft_process(frt_handle h, const float *x_dev, int64_t x_stri
             else FRT_LAUNCH_FAST(FRT_STFT_LOGPOWER, 0);
         }
 #undef FRT_LAUNCH_FAST
+    } else if (pl.n_fft >= 64 && pl.n_fft <= 1024) {
+        const int vec_ok = (((uintptr_t)x_dev & 7) == 0) && ((x_stride & 1) == 0) && ((hop & 1) == 0);
+        const int q = pl.n_fft / 64, gframes = 32 / q;
+        long long blocks = ((total + gframes - 1) / gframes + SMALL_WARPS - 1) / SMALL_WARPS;
+        if (blocks > 2LL * h->sm_count) blocks = 2LL * h->sm_count;
+#define FRT_LAUNCH_SMALL(QQ)                                                                    \
+    launch_small<QQ>(mode, (unsigned)blocks, st, x_dev, x_stride, n_frames, hop, out_dev,        \
+                     out_stride_c, out_stride_f, pl, total, vec_ok)
+        switch (q) {
+            case 1: FRT_LAUNCH_SMALL(1); break;
+            case 2: FRT_LAUNCH_SMALL(2); break;
+            case 4: FRT_LAUNCH_SMALL(4); break;
+            case 8: FRT_LAUNCH_SMALL(8); break;
+            default: FRT_LAUNCH_SMALL(16); break;
+        }
+#undef FRT_LAUNCH_SMALL
+    } else if ((pl.n_fft == 4096 || pl.n_fft == 8192) && (((uintptr_t)x_dev & 7) == 0) &&
+               ((x_stride & 1) == 0) && ((hop & 1) == 0) && !getenv("FRT_STFT_NO_LARGE")) {
+        const int r = pl.n_fft / 2048, ng = LARGE_WARPS / r;
+        long long blocks = (total + ng - 1) / ng;
+        if (blocks > h->sm_count) blocks = h->sm_count;
+        if (r == 2)
+            launch_large<2>(mode, (unsigned)blocks, st, x_dev, x_stride, n_frames, hop, out_dev, out_stride_c,
+                            out_stride_f, pl, total);
+        else
+            launch_large<4>(mode, (unsigned)blocks, st, x_dev, x_stride, n_frames, hop, out_dev, out_stride_c,
+                            out_stride_f, pl, total);
     } else if (pl.n_fft == 4096 || pl.n_fft == 8192 || pl.n_fft == 16384) {
         const int r = pl.n_fft / 2048;
         const int vec_ok = (((uintptr_t)x_dev & 7) == 0) && ((x_stride & 1) == 0) && ((hop & 1) == 0);

@@ -1,5 +1,5 @@
 """GPU parity of the lane-pipelined filterbank kernel (friture_b200/csrc/bank_pipe.cu), every
-variant (32- / 64-sample steps, one / two channels per warp), through the C ABI vs the CPU oracle
+variant (32- / 64-sample steps, one / two channels per lane, two / one section per lane), through the C ABI vs the CPU oracle
 (the reference's IIR bank friture/filter.py:86-118 + friture/octavespectrum.py:101-121)."""
 import os
 import sys
@@ -13,17 +13,19 @@ from test_bank_gpu import energy_rel_err, make_x, oracle_run  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = [(1, 5), (2, 5), (1, 6), (2, 6)]
+# (channels per lane, log2 step, sections per lane)
+VARIANTS = [(1, 5, 2), (2, 5, 2), (1, 6, 2), (2, 6, 2), (1, 5, 1), (2, 5, 1), (1, 6, 1), (2, 6, 1)]
 
 
 @pytest.fixture
 def variant(request):
-    pack, logch = request.param
-    old = {k: os.environ.get(k) for k in ("FRT_BANK_KERNEL", "FRT_BANK_PACK", "FRT_BANK_LOGCH")}
+    pack, logch, spl = request.param
+    old = {k: os.environ.get(k) for k in ("FRT_BANK_KERNEL", "FRT_BANK_PACK", "FRT_BANK_LOGCH", "FRT_BANK_SPL")}
     os.environ["FRT_BANK_KERNEL"] = "pipe"
     os.environ["FRT_BANK_PACK"] = str(pack)
     os.environ["FRT_BANK_LOGCH"] = str(logch)
-    yield pack, logch
+    os.environ["FRT_BANK_SPL"] = str(spl)
+    yield pack, logch, spl
     for k, v in old.items():
         if v is None:
             os.environ.pop(k, None)

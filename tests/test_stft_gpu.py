@@ -158,3 +158,31 @@ def test_plan_cache_alternating_sizes():
         b = pb.stft(xd, hop=1024).cpu().numpy().astype(np.float64)
     assert_logpower_parity(a, fo.log_spectrogram(fo.stft_power_batch(x, 8192, 2048)))
     assert_logpower_parity(b, fo.log_spectrogram(fo.stft_power_batch(x, 4096, 1024)))
+
+
+@pytest.mark.parametrize("n_fft,hop,C,F", [(64, 32, 5, 71), (128, 64, 3, 45), (256, 100, 7, 37), (512, 256, 9, 33),
+                                           (1024, 512, 7, 37), (1024, 333, 2, 19), (4096, 2048, 7, 37),
+                                           (8192, 4096, 5, 23), (8192, 1024, 3, 150), (4096, 1001, 2, 11)])
+def test_ragged_frame_counts_all_kernels(n_fft, hop, C, F):
+    """Frame counts that do not divide into the kernels' frame groups / warps, odd hops (scalar or
+    unaligned-load paths), many channels: every size class against the oracle."""
+    from oracle import friture_oracle as fo
+    x = make_input("randn", C, n_fft + (F - 1) * hop, seed=n_fft + hop)
+    got = run_gpu(x, n_fft, hop, log=False)
+    ref = fo.stft_power_batch(x, n_fft, hop)
+    assert got.shape == ref.shape == (C, F, n_fft // 2 + 1)
+    assert rel_err(got, ref) < TOL
+    got = run_gpu(x, n_fft, hop, log=True)
+    assert_logpower_parity(got, fo.log_spectrogram(ref), min_frac=0.95 if n_fft < 1024 else 0.9999)
+
+
+def test_large_sizes_unaligned_input_falls_back():
+    import torch
+    from friture_b200 import audioproc
+    from oracle import friture_oracle as fo
+    x = make_input("randn", 2, 4096 * 3 + 1, seed=19)
+    proc = audioproc()
+    proc.set_fftsize(4096)
+    xd = torch.from_numpy(x).cuda()[:, 1:]          # 4-byte aligned only
+    got = proc.stft(xd, hop=2048).cpu().numpy().astype(np.float64)
+    assert_logpower_parity(got, fo.log_spectrogram(fo.stft_power_batch(x[:, 1:], 4096, 2048)))
