@@ -524,7 +524,7 @@ class Combined:
         achieved = byts / (kern_ms * 1e-3) / 1e9
         ops = bank_fp32_ops_per_sample(self.n_oct) * self.C * (self.F + 1) * HOP
         issue_peak = SM_COUNT * 128 * SM_MHZ * 1e6
-        r = {"bound": "hbm", "kernel": "bank_pipe_kernel<6,1,3> (30-band filterbank, the step's dominant kernel)",
+        r = {"bound": "hbm", "kernel": "bank_pipe_kernel<6,1,3,2> (30-band filterbank, the step's dominant kernel)",
              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
              "peak_source": peak_src, "algorithmic_bytes_per_launch": byts,
              "bytes_per_unit": byts / (self.C * (self.F + 1)), "kernel_ms": kern_ms,
@@ -802,8 +802,8 @@ def other_workloads(args, dev, rank, world, barrier, peak, peak_src):
         res["combined_channel_sweep"] = sweep
         # the widgets' default FFT sizes (spectrogram 4096, spectrum 8192), 75 % overlap as the widgets use
         from friture_b200 import audioproc
-        x = synth(256, 64 * 1024, dev, 5)
-        for n_fft in (1024, 4096, 8192):
+        x = synth(256, 256 * 1024, dev, 5)
+        for n_fft in (256, 1024, 4096, 8192):
             pw = audioproc()
             pw.set_fftsize(n_fft)
             hopw = n_fft // 4

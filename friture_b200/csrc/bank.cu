@@ -833,8 +833,9 @@ static int bank_process_impl(frt_handle h, const float *x_dev, int64_t x_stride,
         // measured on B200 (blocks/s of 512 samples, 27 bands; steps of 32 / 64 samples, one / two
         // channels per lane): 1024 channels 6.1e7 (32) / 8.7e7 (64); 2048: 9.9e7 / 1.35e8; 4096: 1.04e8 /
         // 1.33e8 / 1.44e8 (32, two per lane); 8192: 1.29e8 / 1.34e8 / 1.44e8.  128-sample steps brought
-        // nothing over 64.  The choice depends on the plan and the block length only, so a stream
-        // gives the same bits however it is cut into launches.
+        // nothing over 64, the one-section-per-lane layout (FRT_BANK_SPL=1) nothing at any channel count
+        // (profiles/r2_bank_variants.txt).  The choice depends on the plan and the block length only, so
+        // a stream gives the same bits however it is cut into launches.
         int pack = pl->n_channels > 3072 ? 2 : 1;
         int logch = (block >= 512 && pl->n_channels <= 3072) ? 6 : 5;
         int spl = 2;

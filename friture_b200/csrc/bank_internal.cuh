@@ -33,7 +33,8 @@ constexpr int PIPE_RX = 8;          // input ring depth (chunks)
 constexpr int PIPE_PF = 4;          // prefetch distance (chunks)
 
 struct PipeParams {
-    float c[PIPE_MAX_SEC], na1[PIPE_MAX_SEC], na2[PIPE_MAX_SEC];   // per role r = section index
+    float c[PIPE_MAX_SEC], na1[PIPE_MAX_SEC], na2[PIPE_MAX_SEC];   // per section
+    float b1[PIPE_MAX_SEC], b2[PIPE_MAX_SEC];                       // c - a1, 1 - a2 (state-space input gains)
     float gband[4];
     float gdec;
     float alpha[BANK_MAX_OCT + 1];

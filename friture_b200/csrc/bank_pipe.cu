@@ -48,9 +48,11 @@ namespace {
 //   SPL = 2  one half-warp per channel (pair), roles as described above, decimator chain 3 lanes deep;
 //   SPL = 1  one WARP per channel (pair): NR = 2 bpo + 6 roles per group, role r = section r, a band is a
 //            chain of two lanes (its output trails the stage input by one step), the decimator a chain
-//            of six.  Half the serial work per lane and step: the kernel is bound by the latency of
-//            one warp's instruction stream up to ~1000 channels (its duration barely moves between 1
-//            and 1024 channels), so this is the layout for few channels.
+//            of six.  Half the arithmetic per lane and step -- but measured no faster (1024 channels:
+//            3.16 ms against 2.76 ms; 256 channels: equal): the step time of a warp is set by
+//            latencies spread over the whole step (shared-memory round trips at the segment
+//            switches, the single dependent chain of a lane, branches), not by the count of section
+//            samples per lane.  Kept as a tested variant (FRT_BANK_SPL=1); the dispatch uses SPL = 2.
 template <int SPL> struct Geo {
     static constexpr int HW = SPL == 2 ? 16 : 32;      // lanes per channel slot
     static constexpr int NSLOT = 32 / HW;               // channel slots per warp
@@ -146,13 +148,33 @@ __device__ __forceinline__ bool opq(bool p) {
     return v != 0;
 }
 
-// normalised biquad step (bank_internal.cuh): y = x + z1; z1 = c x - a1 y + z2; z2 = x - a2 y
+// normalised biquad step (bank_internal.cuh): y = x + z1; z1 = c x - a1 y + z2; z2 = x - a2 y.
+// FRT_PIPE_SSFORM=1 selects the state-space form with y substituted,
+//     z1' = -a1 z1 + (B1 x + z2),  z2' = -a2 z1 + B2 x,   B1 = c - a1,  B2 = 1 - a2,
+// which shortens the loop-carried path (z1 -> z1' is one FFMA) at the price of a fifth operation.
+// Measured on B200 (1024 ch x 128 blocks of 1024, 10 octaves): 2.87 ms against 2.76 ms for the
+// 4-operation form; 8192 channels 14.0 against 13.3 ms -- the step is not bound by this chain alone, the
+// extra instruction costs more than the shorter chain brings.  Default: 4-operation form.
+#ifndef FRT_PIPE_SSFORM
+#define FRT_PIPE_SSFORM 0
+#endif
+// FRT_PIPE_FUSE=1: the smoothing-accumulator updates of step k-1 are issued inside the section loops
+// of step k (2.76 against 2.81 ms).
+#ifndef FRT_PIPE_FUSE
+#define FRT_PIPE_FUSE 1
+#endif
 template <class T>
-__device__ __forceinline__ T biquad(T x, T &z1, T &z2, float cc, float na1, float na2) {
+__device__ __forceinline__ T biquad(T x, T &z1, T &z2, float b1, float b2, float na1, float na2) {
     const T y = v_add(x, z1);
-    const T t = v_fma(cc, x, z2);
+#if FRT_PIPE_SSFORM
+    const T w = v_fma(b1, x, z2);
+    z2 = v_fma(na2, z1, v_mul(b2, x));
+    z1 = v_fma(na1, z1, w);
+#else
+    const T t = v_fma(b1 - na1, x, z2);      // c = b1 + a1
     z1 = v_fma(na1, y, t);
     z2 = v_fma(na2, y, x);
+#endif
     return y;
 }
 
@@ -263,8 +285,9 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
     const bool isdec2 = worker && (r == NR - 1);
     const bool ishead = (d == 0);                            // reads the stage input
     const int maxstage = isband ? n_oct - 1 : n_oct - 2;     // the last stage's decimator is unused (filter.py:113)
-    const float cA = P.c[SPL * r], n1A = P.na1[SPL * r], n2A = P.na2[SPL * r];
-    const float cB = P.c[SPL * r + SPL - 1], n1B = P.na1[SPL * r + SPL - 1], n2B = P.na2[SPL * r + SPL - 1];
+    const float b1A = P.b1[SPL * r], b2A = P.b2[SPL * r], n1A = P.na1[SPL * r], n2A = P.na2[SPL * r];
+    const float b1B = P.b1[SPL * r + SPL - 1], b2B = P.b2[SPL * r + SPL - 1], n1B = P.na1[SPL * r + SPL - 1],
+                n2B = P.na2[SPL * r + SPL - 1];
     const float gb_lane = isband ? P.gband[band] : 0.f;
     const float gdec = P.gdec;
 
@@ -349,14 +372,44 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
     const int k_hi = (n_oct > JR) ? n_chunks : 0;
 
     // ================================================================ phase A: the section loops
+    // The smoothing accumulators of step k-1 (phase B's bulk) are updated INSIDE the section loops of
+    // step k: the section recurrences leave most issue slots of the warp empty, the independent
+    // accumulator updates fill them.  They read the band outputs of step k-1 (buffer (k-1)&1), which
+    // this step only reads as well.
     auto phaseA = [&](int k, auto check_tag) {
         constexpr bool CHECK = decltype(check_tag)::value;
+        const int kp = k - 1, kbp = kp - BSK;      // kbp: the stage-0 chunk whose band outputs step kp wrote
+        const bool bv0 = !CHECK || (kp >= 0 && (unsigned)kbp < (unsigned)n_chunks);
+        bool bvm[NSL];
+#pragma unroll
+        for (int q = 0; q < NSL; q++) {
+            bvm[q] = mok[q];
+            if (CHECK) bvm[q] = bvm[q] && kp >= 0 && (unsigned)(kbp - DEC_DEPTH * mst[q]) < (unsigned)n_chunks;
+        }
+        const T *ybuf = sW + (kp & 1) * CH;
+        constexpr int NUPD = 2 * BPO * NSL;        // accumulator updates per step
+        auto bupd = [&](int i) {                   // i is a compile-time constant after unrolling
+            constexpr int OL = SPL == 2 ? 1 : 2;   // band b's output lane: OL*b + OL-1
+            const int which = i & 1, q = (i >> 1) % NSL, b = (i >> 1) / NSL;
+            const int p = hl + HW * q;
+            // raw units of the normalised sections; the squared chain gain is applied on emission
+            if (which == 0) {
+                const T yv = ybuf[(OL * b + OL - 1) * LY::WSTR + p];
+                if (bv0) acc0[b][q] = v_add(v_fma(-P.aq0, acc0[b][q], acc0[b][q]), v_sq(yv));
+            } else {
+                const T yv = ybuf[(NR + OL * b + OL - 1) * LY::WSTR + p];
+                if (bvm[q]) accm[b][q] = v_add(v_fma(-aqm[q], accm[b][q], accm[b][q]), v_sq(yv));
+            }
+        };
         const int u = k - d;
         // heads read the stage input vector, the other decimator lanes the buffer their predecessor
         // (lane hl-1) filled one step earlier; every lane writes its own region (buffer k&1)
         const T *inp = ishead ? sX + (k & (RX - 1)) * LY::XSLOT + (G ? LY::XM : LY::X0)
                               : sW + (hl - 1) * LY::WSTR + ((k - 1) & 1) * CH;
-        T *outp = sW + hl * LY::WSTR + (k & 1) * CH;
+        // lanes beyond the two groups are exact clones of lane 0 (same role, same state, same
+        // addresses): they run the section loops only to take part in the accumulator updates, and
+        // store the same values to the same places, so no store needs a branch
+        T *outp = sW + (worker ? hl : 0) * LY::WSTR + (k & 1) * CH;
         T *xn = sX + ((k + 1) & (RX - 1)) * LY::XSLOT + LY::XM + G * (CH / 2);
         const bool pv0 = !CHECK || ((unsigned)u < (unsigned)n_chunks && 0 <= maxstage);
         // ruler slot: the stage >= JR whose sample is due (group 1 only)
@@ -422,11 +475,15 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
                             pvc = pvR;
                         }
                     }
-                    const T ya = biquad(v[q][i], cur[0], cur[1], cA, n1A, n2A);
-                    if (SPL == 2) y[i] = biquad(ya, cur[RS - 2], cur[RS - 1], cB, n1B, n2B);
+                    const T ya = biquad(v[q][i], cur[0], cur[1], b1A, b2A, n1A, n2A);
+                    if (SPL == 2) y[i] = biquad(ya, cur[RS - 2], cur[RS - 1], b1B, b2B, n1B, n2B);
                     else y[i] = ya;
                 }
                 const int gq = b0 + q;
+#if FRT_PIPE_FUSE
+#pragma unroll
+                for (int i = gq * NUPD / NG; i < (gq + 1) * NUPD / NG; i++) bupd(i);
+#endif
                 if (gq < NG - 1) {
                     if (!isdec2) st4(outp + 4 * gq, y);
                     else st2(xn + 2 * gq, v_mul(gdec, y[0]), v_mul(gdec, y[2]));
@@ -457,6 +514,10 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
                 }
             }
         }
+#if !FRT_PIPE_FUSE
+#pragma unroll
+        for (int i = 0; i < NUPD; i++) bupd(i);
+#endif
         const bool ge = opq(G != 0);
         if (ge && pvc) {
 #pragma unroll
@@ -466,30 +527,12 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
         for (int e = 0; e < RS; e++) zc[e] = v_sel(!ge && pv0, cur[e], zc[e]);
     };
 
-    // ================================================================ phase B: smoothing, prefetch
+    // ================================================================ phase B of step k (run after the
+    // section loops of step k+1, which carried its accumulator updates): block ends, flush
     auto phaseB = [&](int k, auto check_tag) {
         constexpr bool CHECK = decltype(check_tag)::value;
-        const int kb = k - BSK;        // the stage-0 chunk whose band outputs were written in this step
-        const bool valid0 = !CHECK || (unsigned)kb < (unsigned)n_chunks;
-        bool vm[NSL];
-#pragma unroll
-        for (int q = 0; q < NSL; q++) {
-            vm[q] = mok[q];
-            if (CHECK) vm[q] = vm[q] && (unsigned)(kb - DEC_DEPTH * mst[q]) < (unsigned)n_chunks;
-        }
-#pragma unroll
-        for (int b = 0; b < BPO; b++) {
-            constexpr int OL = SPL == 2 ? 1 : 2;                           // band b's output lane: OL*b + OL-1
-            const T *y0p = sW + (OL * b + OL - 1) * LY::WSTR + (k & 1) * CH;            // group 0 / group 1
-            const T *ymp = sW + (NR + OL * b + OL - 1) * LY::WSTR + (k & 1) * CH;
-            // raw units of the normalised sections; the squared chain gain is applied on emission
-#pragma unroll
-            for (int q = 0; q < NSL; q++) {
-                const int p = hl + HW * q;
-                if (valid0) acc0[b][q] = v_add(v_fma(-P.aq0, acc0[b][q], acc0[b][q]), v_sq(y0p[p]));
-                if (vm[q]) accm[b][q] = v_add(v_fma(-aqm[q], accm[b][q], accm[b][q]), v_sq(ymp[p]));
-            }
-        }
+        const int kb = k - BSK;        // the stage-0 chunk whose band outputs were written in step k
+        const bool valid0 = !CHECK || (k >= 0 && (unsigned)kb < (unsigned)n_chunks);
         // ---- block ends (warp-uniform conditions: they depend on the step only)
         if (valid0 && (((kb + 1) & nbmask) == 0)) {    // stage 0: weighted sum of its CH accumulators
             const int blk = ((kb + 1) >> lognb) - 1;
@@ -581,20 +624,26 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
                 }
             }
         }
-        prefetch(k + PF);
-        cp_async_wait<PF - 1>();           // chunk k+1 has landed
     };
 
-    for (int k = 0; k < n_steps; k++) {
-        const bool fast = k >= k_lo && k < k_hi;
-        if (worker) {
-            if (fast) phaseA(k, std::false_type());
-            else phaseA(k, std::true_type());
-        }
+    // iteration k = section loops of step k (+ accumulator updates of step k-1), block ends / flush of
+    // step k-1, prefetch; one extra iteration finishes the last step.  The steps whose every slot is
+    // valid (and whose predecessor's are) run in their own tight loop without the range checks.
+    auto iteration = [&](int k, auto check_tag) {
+        phaseA(k, check_tag);
+        phaseB(k - 1, check_tag);
+        prefetch(k + PF);
+        cp_async_wait<PF - 1>();           // chunk k+1 has landed
         __syncwarp();
-        if (fast) phaseB(k, std::false_type());
-        else phaseB(k, std::true_type());
-        __syncwarp();
+    };
+    const int total = n_steps + 1;
+    const int fast_lo = min(k_lo + 1, total);
+    const int fast_hi = max(fast_lo, min(k_hi, total));
+    for (int ph = 0; ph < 2; ph++) {
+        const int ka = ph ? fast_hi : 0, kz = ph ? total : fast_lo;
+        for (int k = ka; k < kz; k++) iteration(k, std::true_type());
+        if (ph == 0)
+            for (int k = fast_lo; k < fast_hi; k++) iteration(k, std::false_type());
     }
 
     // ---- epilogue: the pipeline is drained, every stage ended on a block boundary
@@ -717,6 +766,8 @@ void frt_pipe_prepare(BankPlan *pl) {
             P.c[r] = B.coef[r][1];
             P.na1[r] = -B.coef[r][3];
             P.na2[r] = -B.coef[r][4];
+            P.b1[r] = B.coef[r][5];      // c - a1, rounded once from double (frt_bank_plan)
+            P.b2[r] = B.coef[r][6];      // 1 - a2
         }
         for (int b = 0; b < B.bpo; b++) P.gband[b] = B.gband[b];
         P.gdec = B.gdec;
@@ -746,7 +797,8 @@ bool frt_pipe_supported(const BankPlan *pl, int block, int logch, int spl) {
     const int nb = block >> logch;                      // steps per block
     const int ring = spl == 1 ? EnRing<1>::N : EnRing<2>::N;
     // blocks staged but not yet flushed when a block's vector leaves, plus the one being written
-    return (P.fdelta + nb - 1) / nb + 1 <= ring;
+    // (+1: the section loops of the next step already stage energies while a block is flushed)
+    return (P.fdelta + nb - 1) / nb + 2 <= ring;
 }
 
 cudaError_t frt_pipe_launch(const BankPlan *pl, BankArgs a, int logch, int pack, int spl, cudaStream_t st) {
