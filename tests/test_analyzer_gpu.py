@@ -125,3 +125,25 @@ def test_gather_of_columns_two_ranks(tmp_path):
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert out.stdout.count("RESULT nccl-auto rank") == 2
     assert out.stdout.count("RESULT peer-ce rank") == 2 and out.stdout.count("RESULT peer-kernel rank") == 2
+
+
+def test_peer_push_kernel_single_gpu():
+    """frt_peer_push with local buffers standing in for the peers': every destination receives the
+    block, bytes outside it stay untouched, odd sizes that are not a multiple of the grid stride work."""
+    import ctypes
+    from ctypes import c_size_t, c_void_p
+    import torch
+    from friture_b200 import _lib
+    h = _lib.default_handle()
+    n = 3 * 1000 * 1025 + 4                      # floats; 16-byte multiple, not a multiple of anything else
+    src = torch.randn(n, device="cuda")
+    dsts = [torch.full((n + 8,), -7.0, device="cuda") for _ in range(3)]
+    table = (c_void_p * 3)(*[d.data_ptr() + 16 for d in dsts])      # offset by 4 floats, still 16-byte aligned
+    st = torch.cuda.current_stream()
+    h.call("frt_peer_push", c_void_p(src.data_ptr()), table, 3, c_size_t(n * 4), 0, c_void_p(st.cuda_stream))
+    torch.cuda.synchronize()
+    for d in dsts:
+        assert torch.equal(d[4:4 + n], src)
+        assert float(d[:4].max()) == -7.0 and float(d[4 + n:].min()) == -7.0
+    with pytest.raises(_lib.FrtError):
+        h.call("frt_peer_push", c_void_p(src.data_ptr() + 4), table, 3, c_size_t(n * 4), 0, c_void_p(st.cuda_stream))
