@@ -5,6 +5,8 @@
 // y**2, exp_smoothed_value, 10*log10 + weighting).  The stream is cut into time segments; the H2D
 // copy of segment s+1, the two kernels of segment s and the D2H copy of segment s-1 overlap.  All channels go through every launch: the filterbank's
 // parallelism is the channel axis.
+#include <cstdlib>
+
 #include "frt_internal.cuh"
 
 namespace {
@@ -98,12 +100,19 @@ extern "C" int frt_combined_process_host(frt_handle h, const float *x_host, int6
                          sizeof(float) * (size_t)n_channels * B * nbands);
     if (rc) return rc;
     CombPipe &p = *reinterpret_cast<CombPipe *>(h->comb);
-    // the first segment's H2D and the last segment's D2H are not overlapped with anything: short
-    // segments keep that exposed part small (measured at 1024 ch x 129 blocks: 8 segments 13.1 ms,
-    // PCIe moving 0.54 GB in and 0.55 GB out)
-    int nseg = B >= 128 ? 32 : (B >= 64 ? 16 : (B >= 8 ? 4 : 1));
+    // the first segment's H2D and the last segment's D2H are not overlapped with anything, short
+    // segments keep that exposed part small; very short ones cost more in 2-D copy rows and kernel
+    // launches than they save.  Measured at 1024 ch x 129 blocks (0.54 GB in, 0.55 GB out;
+    // tools/perf_e2e.py): 4 segments 14.8 ms, 8: 13.5, 12: 13.0, 16: 12.9, 24: 14.7, 32: 15.0
+    int nseg = B >= 128 ? 16 : (B >= 64 ? 8 : (B >= 8 ? 4 : 1));
+    if (const char *e = getenv("FRT_COMB_NSEG")) {      // tuning knob
+        const int v = atoi(e);
+        if (v >= 1 && v <= MAX_SEG) nseg = v;
+    }
+    if (nseg > B) nseg = (int)B;
     const int64_t seg_blocks = (B + nseg - 1) / nseg;
     int64_t f_done = 0;
+    int last = 0;
     for (int s = 0; s < nseg; s++) {
         const int64_t b0 = s * seg_blocks, b1 = (b0 + seg_blocks < B) ? b0 + seg_blocks : B;
         if (b0 >= b1) break;
@@ -135,13 +144,15 @@ extern "C" int frt_combined_process_host(frt_handle h, const float *x_host, int6
                                           p.d_spec + f_done * nbins, sizeof(float) * F * nbins,
                                           sizeof(float) * (f1 - f_done) * nbins, n_channels,
                                           cudaMemcpyDeviceToHost, p.s_out));
-        FRT_CUDA(h, cudaStreamWaitEvent(p.s_out, p.ev_bank[s], 0));
-        FRT_CUDA(h, cudaMemcpy2DAsync(bands_host + b0 * nbands, sizeof(float) * B * nbands,
-                                      p.d_bands + b0 * nbands, sizeof(float) * B * nbands,
-                                      sizeof(float) * (b1 - b0) * nbands, n_channels,
-                                      cudaMemcpyDeviceToHost, p.s_out));
         if (f1 > f_done) f_done = f1;
+        last = s;
     }
+    // the band vectors (C x B x nbands, 1.5 % of the output) leave in ONE contiguous copy at the end: cut
+    // per segment they are C rows of a few hundred bytes each, which costs the copy engine more time
+    // than the spectrogram columns next to them
+    FRT_CUDA(h, cudaStreamWaitEvent(p.s_out, p.ev_bank[last], 0));
+    FRT_CUDA(h, cudaMemcpyAsync(bands_host, p.d_bands, sizeof(float) * (size_t)n_channels * B * nbands,
+                                cudaMemcpyDeviceToHost, p.s_out));
     FRT_CUDA(h, cudaStreamSynchronize(p.s_out));
     FRT_CUDA(h, cudaStreamSynchronize(p.s_stft));
     FRT_CUDA(h, cudaStreamSynchronize(p.s_bank));
