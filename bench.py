@@ -450,7 +450,7 @@ class Combined:
         # our kernels per step (copy-engine pushes / NCCL kernels are not ours, the push kernel is)
         self.launches_per_step = (1 + self.n_chunks) if self.gather else 2
         if self.gather and self.transport == "peer" and (self.engine == "kernel" or
-                                                         (self.engine == "auto" and world > 2)):
+                                                         (self.engine == "auto" and world > 4)):
             self.launches_per_step += self.n_chunks
         self.bank_events = []
 
@@ -829,7 +829,7 @@ def other_workloads(args, dev, rank, world, barrier, peak, peak_src):
         # reduction (one smoothed column per channel and tick instead of one per frame)
         res["combined_no_gather"] = quick(Combined, args.channels, args.frames, dev, rank, world, barrier, peak,
                                           peak_src, reps=5, gather=False)
-        auto = "peer-ce" if world <= 2 else "peer-kernel"
+        auto = "peer-ce" if world <= 4 else "peer-kernel"
         for other in ("nccl", "peer-ce", "peer-kernel"):
             if other != args.transport and not (args.transport == "peer" and other == auto):
                 res["combined_gather_via_%s" % other] = quick(Combined, args.channels, args.frames, dev, rank, world,
@@ -899,7 +899,7 @@ def main():
     ap.add_argument("--no-gather", action="store_true", help="N > 1: leave the all-gather out of the step")
     ap.add_argument("--transport", default="peer", choices=["peer", "peer-ce", "peer-kernel", "nccl"],
                     help="N > 1: one-hop pushes over NVLink peer memory (default; copy engines at 2 GPUs, a copy "
-                         "kernel from 4 up) or NCCL all-gather")
+                         "kernel above 4) or NCCL all-gather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-others", action="store_true")

@@ -129,7 +129,7 @@ class ChannelAnalyzer:
         filterbank after them; the two compute kernels are NOT run side by side (see process()).
 
         transport="peer"  one-hop pushes into the peers' IPC-opened buffers over NVLink (friture_b200/peer.py):
-                          copy engines at 2 GPUs, a small copy kernel from 4 GPUs up (engine="ce"|"kernel").  The gathered array [n_chunks, world, C, F/n_chunks, nbins]
+                          copy engines up to 4 GPUs, a small copy kernel above (engine="ce"|"kernel").  The gathered array [n_chunks, world, C, F/n_chunks, nbins]
                           belongs to the analyzer (`self.peer_gather.gathered`); call
                           `self.peer_gather.wait_all()` before reading other ranks' columns.
         transport="nccl"  torch.distributed all_gather_into_tensor per chunk on a side stream into

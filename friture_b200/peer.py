@@ -9,8 +9,9 @@ step for 0.7 ms of link time).  Here every rank allocates its gathered buffer th
 the 64-byte handles, open each other's buffers, and every rank PUSHES its own block into its peers'
 buffers with ``cudaMemcpyAsync`` on one stream per peer: the copy engines drive NVLink/NVSwitch, no
 SM is involved, and the transfers overlap the compute for free.  The copy engines of one GPU top out
-near 430 GB/s (measured at N = 8, where 7/8 of 4.3 GB must leave every GPU per step), so from 4 GPUs
-up the push is done by ``frt_peer_push`` instead: 64 CTAs that read the block once from local HBM and
+near 430-510 GB/s (measured at N = 8, where 7/8 of 4.3 GB must leave every GPU per step: 8.66 ms; at
+N = 4 they still keep up: 3.17 ms against 3.08 ms of compute), so above 4 GPUs the push is done by
+``frt_peer_push`` instead: 64 CTAs that read the block once from local HBM and
 store it to all peers with 128-bit stores -- one hop, no ring steps, a few warps' worth of issue
 slots (measured at N = 8, 1024 channels x 128 hops per GPU, tools/perf_gather.py: 6.15 ms per step and
 611 GB/s received per GPU, against 7.08 ms with NCCL and 8.66 ms with the copy engines).  The rank's own block is written in place by the STFT kernel (``local(i)`` is a view of the
@@ -61,10 +62,11 @@ class PeerGather:
         self._ptr = p.value
         self.gathered = torch.as_tensor(_DevBuf(self._ptr, (self.n_blocks, self.world) + self.block_shape),
                                         device=self.device)
-        # "ce": one cudaMemcpyAsync per peer (copy engines, no SM at all; ~430 GB/s per GPU measured,
-        # the best choice at 2 GPUs); "kernel": frt_peer_push, a small copy kernel that reads the block
-        # once and stores it to every peer (fills the links from 4 GPUs up)
-        self.engine = ("ce" if self.world <= 2 else "kernel") if engine == "auto" else engine
+        # "ce": one cudaMemcpyAsync per peer (copy engines, no SM at all; 430-510 GB/s per GPU measured:
+        # enough up to 4 GPUs, where the step stays at the compute time); "kernel": frt_peer_push, a
+        # small copy kernel that reads the block once and stores it to every peer (611 GB/s at 8 GPUs;
+        # at 4 GPUs its CTAs cost the filterbank more than the copy engines' lower rate: 4.76 vs 3.17 ms)
+        self.engine = ("ce" if self.world <= 4 else "kernel") if engine == "auto" else engine
         self.n_ctas = int(n_ctas)
         self._peers = [None] * self.world
         self._streams = [None] * self.world

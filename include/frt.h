@@ -176,7 +176,7 @@ int frt_peer_close(frt_handle h, void *peer_ptr);
 int frt_peer_copy(frt_handle h, void *dst, const void *src, size_t bytes, void *stream);
 /* One-hop push of a block into the same offset of n_peers (<= 15) opened peer buffers by a small copy
  * kernel (n_ctas CTAs, 0 = 64): the block is read once from local HBM and stored to every peer
- * over NVLink with 128-bit stores.  Faster than the copy engines from 4 GPUs up.                  */
+ * over NVLink with 128-bit stores.  Faster than the copy engines at 8 GPUs (not at 2 or 4).                  */
 int frt_peer_push(frt_handle h, const void *src, void *const *peer_dst, int n_peers, size_t bytes,
                   int n_ctas, void *stream);
 
