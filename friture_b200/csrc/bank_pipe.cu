@@ -163,6 +163,11 @@ __device__ __forceinline__ bool opq(bool p) {
 #ifndef FRT_PIPE_FUSE
 #define FRT_PIPE_FUSE 1
 #endif
+// FRT_PIPE_EVMASK=1: one bit test per step instead of a compare-and-branch per stage for the rare
+// block-end / flush work (see `evmask` in the kernel).
+#ifndef FRT_PIPE_EVMASK
+#define FRT_PIPE_EVMASK 1
+#endif
 template <class T>
 __device__ __forceinline__ T biquad(T x, T &z1, T &z2, float b1, float b2, float na1, float na2) {
     const T y = v_add(x, z1);
@@ -629,9 +634,24 @@ bank_pipe_kernel(const __grid_constant__ PipeParams P, const BankArgs a) {
     // iteration k = section loops of step k (+ accumulator updates of step k-1), block ends / flush of
     // step k-1, prefetch; one extra iteration finishes the last step.  The steps whose every slot is
     // valid (and whose predecessor's are) run in their own tight loop without the range checks.
+    // Block ends and flushes happen at fixed phases of the step counter modulo the steps per block
+    // (stage j's blocks end DEC_DEPTH*j steps after stage 0's, the flush fdelta steps after): one
+    // bit test per step decides whether phase B has anything to do at all, instead of one compare
+    // and branch per stage (each costs a lone warp ~20 cycles of branch latency).  The mask only
+    // filters; phase B evaluates its own conditions.
+    const int NBS = nbmask + 1;
+    unsigned long long evmask = ~0ull;
+    if (FRT_PIPE_EVMASK && NBS <= 64) {
+        evmask = 0;
+        evmask |= 1ull << (BSK & nbmask);
+        for (int j = 1; j <= LOGCH && j <= n_oct - 1; j++) evmask |= 1ull << ((BSK + DEC_DEPTH * j) & nbmask);
+        evmask |= 1ull << (fdelta & nbmask);
+    }
+    const bool ev_always = !(FRT_PIPE_EVMASK && NBS <= 64);
     auto iteration = [&](int k, auto check_tag) {
+        constexpr bool CHECK = decltype(check_tag)::value;
         phaseA(k, check_tag);
-        phaseB(k - 1, check_tag);
+        if (CHECK || ev_always || ((evmask >> (k & nbmask)) & 1ull)) phaseB(k - 1, check_tag);
         prefetch(k + PF);
         cp_async_wait<PF - 1>();           // chunk k+1 has landed
         __syncwarp();
