@@ -118,6 +118,16 @@ class ChannelAnalyzer:
                          int(self.hop), _lib._ptr(spec_host), _lib._ptr(bands_host), int(self.nbands), 1)
         return spec_host, bands_host
 
+    def close(self):
+        """Release the peer-memory gather buffers (collective: every rank of the group must call it).
+        Only needed when an analyzer that used `process_sharded(transport="peer")` is dropped long
+        before the process ends; the buffers are otherwise freed with the process."""
+        pg = getattr(self, "peer_gather", None)
+        if pg is not None:
+            pg.close()
+            self.peer_gather = None
+            self._pg_key = None
+
     # ------------------------------------------------------------------ multi-GPU path
     def process_sharded(self, x, gathered=None, spec_chunks=None, bands=None, n_chunks=8, group=None,
                         transport="peer", engine="auto"):
